@@ -1,0 +1,314 @@
+// pivchol.cu -- pivoted-Cholesky preconditioner: greedy partial Cholesky, Woodbury factor, N(0,P) probes.
+//
+// gp_pivoted_cholesky restates linear_operator.functions._pivoted_cholesky (SURVEY.md Appendix A.3;
+// surfaced at /root/reference/gpytorch/__init__.py:146-173): k sequential steps, each picks the largest
+// remaining diagonal entry (ties -> earliest position in the running permutation, as torch.max over
+// permuted_diags does), evaluates ONE kernel row on the fly, and applies the rank-m update.
+// gp_precond_build restates AddedDiagLinearOperator._init_cache_for_constant_diag (Appendix A.4)
+// through the k x k Cholesky of (L^T L + sigma^2 I) in fp64 instead of a QR of [L; sigma I]:
+// W = L C^{-T} spans the same column space as Q[:n] with W W^T == Q Q^T, and
+// log det P = log det(L^T L + sigma^2 I) + (n - k) log sigma^2.
+#include "gp_common.cuh"
+
+namespace gp {
+
+struct PcState {
+  int done;        // stop rule fired (error <= tol) -> later launches are no-ops
+  int rank;        // steps completed
+  int pivot;       // current pivot (global row)
+  int nan_flag;
+  float dpiv;      // sqrt(max diag) = L[m][pivot]
+  float orig_err;  // max of the initial diagonal
+  float err;
+};
+
+constexpr int PC_SEL_THREADS = 1024;
+
+// single CTA: error check + argmax over the not-yet-pivoted entries + permutation swap
+__global__ void __launch_bounds__(PC_SEL_THREADS)
+pc_select_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, int m, float tol,
+                 PcState* __restrict__ st, int64_t* __restrict__ piv_out) {
+  if (st->done) return;
+  __shared__ float s_val[PC_SEL_THREADS];
+  __shared__ int s_pos[PC_SEL_THREADS];
+  __shared__ double s_sum[PC_SEL_THREADS];
+  const int tid = threadIdx.x;
+  float best = -INFINITY;
+  int best_pos = 0x7fffffff;
+  double asum = 0.0;
+  bool nan_seen = false;
+  for (int64_t j = tid; j < n; j += PC_SEL_THREADS) {
+    int pj = pos[j];
+    if (pj < m) continue;  // already a pivot
+    float v = diag[j];
+    if (v != v) nan_seen = true;
+    asum += fabs((double)v);
+    if (v > best || (v == best && pj < best_pos)) { best = v; best_pos = pj; }
+  }
+  if (nan_seen) { best = INFINITY; best_pos = -1; }
+  s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
+  __syncthreads();
+  for (int s = PC_SEL_THREADS / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
+      if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
+      s_sum[tid] += s_sum[tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float mx = s_val[0];
+    int pp = s_pos[0];
+    if (pp < 0 || !(mx > 0.f)) {  // NaN or non-positive pivot: the reference ends up with NaNs in L
+      st->nan_flag = 1;
+      st->done = 1;
+      st->rank = m;
+      return;
+    }
+    if (m == 0) st->orig_err = mx;
+    float err = (float)(s_sum[0] / (double)st->orig_err);
+    st->err = err;
+    if (m > 0 && !(err > tol)) {  // while (m == 0) or (m < max_iter and max(errors) > error_tol)
+      st->done = 1;
+      st->rank = m;
+      return;
+    }
+    // swap perm[m] <-> perm[pp]
+    int pi_new = perm[pp];
+    int pi_old = perm[m];
+    perm[m] = pi_new; perm[pp] = pi_old;
+    pos[pi_new] = m; pos[pi_old] = pp;
+    st->pivot = pi_new;
+    st->dpiv = sqrtf(mx);
+    st->rank = m + 1;
+    piv_out[m] = (int64_t)pi_new;
+  }
+}
+
+// row update: L[m][j] = (K[pi, j] - sum_{q<m} L[q][pi] L[q][j]) / L[m][pi] ; diag[j] -= L[m][j]^2
+template <int KIND>
+__global__ void pc_update_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict__ Lt, int64_t n, int m,
+                                 float* __restrict__ diag, const int* __restrict__ pos, const PcState* __restrict__ st) {
+  if (st->done) return;
+  extern __shared__ float sh[];
+  float* zp = sh;           // [DP]
+  float* lp = sh + DP;      // [m]   L[q][pivot]
+  const int pi = st->pivot;
+  const float dpiv = st->dpiv;
+  for (int c = threadIdx.x; c < DP; c += blockDim.x) zp[c] = Z[(int64_t)pi * DP + c];
+  for (int q = threadIdx.x; q < m; q += blockDim.x) lp[q] = Lt[(int64_t)q * n + pi];
+  __syncthreads();
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float* Lm = Lt + (int64_t)m * n;
+  const int pj = pos[j];
+  if (pj < m) { Lm[j] = 0.f; return; }       // earlier pivots stay zero in this row
+  if (pj == m) { Lm[j] = dpiv; return; }     // the pivot itself
+  float s = 0.f;
+  for (int c = 0; c < DP; ++c) {
+    float df = zp[c] - Z[j * DP + c];
+    s = fmaf(df, df, s);
+  }
+  float v = os * cov_from_arg<KIND>(-0.5f * s);
+  for (int q = 0; q < m; ++q) v = fmaf(-lp[q], Lt[(int64_t)q * n + j], v);
+  v /= dpiv;
+  Lm[j] = v;
+  diag[j] -= v * v;
+}
+
+__global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, float os,
+                               PcState* __restrict__ st) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) { st->done = 0; st->rank = 0; st->pivot = 0; st->nan_flag = 0; st->dpiv = 0.f; st->orig_err = 1.f; st->err = 0.f; }
+  if (j >= n) return;
+  diag[j] = os;  // _approx_diagonal of a stationary kernel
+  perm[j] = (int)j;
+  pos[j] = (int)j;
+}
+
+// ---- preconditioner factor ---------------------------------------------------------------------
+// Gpart[z][a][b] = sum_{j in slice z} L[a][j] L[b][j]   (fp64)
+__global__ void gram_kernel(const float* __restrict__ Lt, int k, int64_t n, int64_t jslice, double* __restrict__ Gpart) {
+  __shared__ float A[16][65];
+  __shared__ float B[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+  const int64_t j_begin = (int64_t)blockIdx.z * jslice, j_end = min(n, j_begin + jslice);
+  double acc = 0.0;
+  for (int64_t j0 = j_begin; j0 < j_end; j0 += 64) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int r = e >> 6, cc = e & 63;
+      int64_t j = j0 + cc;
+      A[r][cc] = (a0 + r < k && j < j_end) ? Lt[(int64_t)(a0 + r) * n + j] : 0.f;
+      B[r][cc] = (b0 + r < k && j < j_end) ? Lt[(int64_t)(b0 + r) * n + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cc = 0; cc < 64; ++cc) acc = fma((double)A[ty][cc], (double)B[tx][cc], acc);
+  }
+  if (a0 + ty < k && b0 + tx < k) Gpart[((int64_t)blockIdx.z * k + a0 + ty) * k + b0 + tx] = acc;
+}
+
+// single CTA: G = sum_z Gpart + noise I ; in-place lower Cholesky C ; logdet
+__global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int k, double noise, int64_t n,
+                                  double* __restrict__ C, double* __restrict__ logdet_out, int* __restrict__ fail) {
+  extern __shared__ double G[];  // [k][k]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < k * k; e += blockDim.x) {
+    double s = 0.0;
+    for (int z = 0; z < nz; ++z) s += Gpart[(int64_t)z * k * k + e];
+    if (e / k == e % k) s += noise;
+    G[e] = s;
+  }
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (tid == 0) {
+      double d = G[j * k + j];
+      if (!(d > 0.0)) { *fail = 1; d = 1e-300; }
+      G[j * k + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double djj = G[j * k + j];
+    for (int i = j + 1 + tid; i < k; i += blockDim.x) G[i * k + j] /= djj;
+    __syncthreads();
+    // trailing update: G[i][l] -= G[i][j] G[l][j] for j < l <= i
+    const int rem = k - j - 1;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      int i = j + 1 + e / rem, l = j + 1 + e % rem;
+      if (l <= i) G[i * k + l] -= G[i * k + j] * G[l * k + j];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < k * k; e += blockDim.x) C[e] = (e % k <= e / k) ? G[e] : 0.0;
+  if (tid == 0) {
+    double ld = 0.0;
+    for (int j = 0; j < k; ++j) ld += log(G[j * k + j]);
+    *logdet_out = 2.0 * ld + (double)(n - k) * log(noise);
+  }
+}
+
+// W[r][:] = solve(C, L[:, r])  (forward substitution, fp64, one thread per row; C in smem)
+__global__ void wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
+                              const double* __restrict__ C, float* __restrict__ W) {
+  extern __shared__ double Cs[];  // [k][k]
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cs[e] = C[e];
+  __syncthreads();
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_local) return;
+  double w[128];
+  for (int a = 0; a < k; ++a) {
+    double s = (double)Lt[(int64_t)a * n_total + row_begin + r];
+    for (int b = 0; b < a; ++b) s -= Cs[a * k + b] * w[b];
+    w[a] = s / Cs[a * k + a];
+  }
+  for (int a = 0; a < k; ++a) W[r * k + a] = (float)w[a];
+}
+
+// Z[r][c] = sum_a L[a][r] eps1[a][c] + sigma eps2[r][c]
+__global__ void probes_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
+                              const float* __restrict__ eps1, const float* __restrict__ eps2, int tp, float sigma,
+                              float* __restrict__ Z) {
+  extern __shared__ float e1[];  // [k][tp]
+  for (int e = threadIdx.x; e < k * tp; e += blockDim.x) e1[e] = eps1[e];
+  __syncthreads();
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_local * tp) return;
+  int64_t r = idx / tp;
+  int c = (int)(idx % tp);
+  float s = sigma * eps2[r * tp + c];
+  for (int a = 0; a < k; ++a) s = fmaf(Lt[(int64_t)a * n_total + row_begin + r], e1[a * tp + c], s);
+  Z[r * tp + c] = s;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float* Lt, int64_t* piv, int* rank_out) {
+  GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(p->same, GP_E_SHAPE, "pivoted Cholesky needs a square operator");
+  const int64_t n = p->n2;
+  GP_REQUIRE(n < (int64_t)1 << 31, GP_E_SHAPE, "n too large");
+  rank = (int)std::min<int64_t>(rank, n);
+  GP_REQUIRE(rank >= 1, GP_E_SHAPE, "rank must be >= 1");
+  cudaStream_t st = p->stream;
+  GP_CHECK(p->pcdiag.ensure(sizeof(float) * n));
+  GP_CHECK(p->pcperm.ensure(sizeof(int) * n));
+  GP_CHECK(p->pcpos.ensure(sizeof(int) * n));
+  GP_CHECK(p->pcstate.ensure(sizeof(PcState)));
+  float* diag = p->pcdiag.as<float>();
+  int* perm = p->pcperm.as<int>();
+  int* pos = p->pcpos.as<int>();
+  PcState* S = p->pcstate.as<PcState>();
+  const unsigned gb = (unsigned)cdiv(n, 256);
+  pc_init_kernel<<<gb, 256, 0, st>>>(diag, perm, pos, n, p->outputscale, S);
+  GP_CUDA(cudaMemsetAsync(Lt, 0, sizeof(float) * (size_t)rank * n, st));
+  GP_CUDA(cudaMemsetAsync(piv, 0, sizeof(int64_t) * rank, st));
+  p->launches += 1;
+  const float* Z = p->Z2.as<float>();
+  for (int m = 0; m < rank; ++m) {
+    pc_select_kernel<<<1, PC_SEL_THREADS, 0, st>>>(diag, perm, pos, n, m, error_tol, S, piv);
+    size_t sh = sizeof(float) * (p->DP + m);
+    switch (p->kind) {
+      case GP_RBF: pc_update_kernel<GP_RBF><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
+      case GP_MATERN12: pc_update_kernel<GP_MATERN12><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
+      case GP_MATERN32: pc_update_kernel<GP_MATERN32><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
+      default: pc_update_kernel<GP_MATERN52><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
+    }
+    p->launches += 2;
+  }
+  GP_CUDA(cudaGetLastError());
+  PcState* hs = reinterpret_cast<PcState*>(reinterpret_cast<char*>(p->pinned) + 2048);
+  GP_CUDA(cudaMemcpyAsync(hs, S, sizeof(PcState), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(cudaStreamSynchronize(st));
+  if (rank_out) *rank_out = hs->rank;
+  if (hs->nan_flag) {
+    set_error("NaNs encountered in preconditioner computation. Attempting to continue without preconditioning.");
+    return GP_W_PIVCHOL_NAN;
+  }
+  return GP_OK;
+}
+
+extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, double* logdet_out) {
+  GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(k >= 1 && k <= 128, GP_E_SHAPE, "preconditioner rank %d not in [1,128]", k);
+  GP_REQUIRE(p->noise > 0.f, GP_E_SHAPE, "preconditioner needs noise > 0");
+  cudaStream_t st = p->stream;
+  const int64_t n = p->n2;
+  const int nz = (int)std::min<int64_t>(16, std::max<int64_t>(1, n / 4096));
+  const int64_t jslice = cdiv(cdiv(n, nz), 64) * 64;
+  GP_CHECK(p->gram.ensure(sizeof(double) * (size_t)nz * k * k));
+  GP_CHECK(p->cholC.ensure(sizeof(double) * (size_t)k * k + 64));
+  double* C = p->cholC.as<double>();
+  double* d_logdet = C + (size_t)k * k;
+  int* d_fail = reinterpret_cast<int*>(d_logdet + 1);
+  GP_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+  dim3 gg((unsigned)cdiv(k, 16), (unsigned)cdiv(k, 16), (unsigned)nz);
+  gram_kernel<<<gg, 256, 0, st>>>(Lt, k, n, jslice, p->gram.as<double>());
+  size_t shc = sizeof(double) * (size_t)k * k;
+  GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, (double)p->noise, n, C, d_logdet, d_fail);
+  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 128), 128, shc, st>>>(Lt, k, n, p->row_begin, p->row_count, C, W);
+  p->launches += 3;
+  GP_CUDA(cudaGetLastError());
+  double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(p->pinned) + 3072);
+  GP_CUDA(cudaMemcpyAsync(h, d_logdet, sizeof(double) + sizeof(int), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(cudaStreamSynchronize(st));
+  if (logdet_out) *logdet_out = h[0];
+  int fail = *reinterpret_cast<int*>(h + 1);
+  GP_REQUIRE(!fail, GP_W_PIVCHOL_NAN, "preconditioner Gram matrix is not positive definite");
+  return GP_OK;
+}
+
+extern "C" int gp_precond_probes(gp_plan* p, const float* Lt, int k, const float* eps1, const float* eps2, int tp, float* Z) {
+  GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(k >= 1 && tp >= 1 && (size_t)k * tp * 4 <= 40 * 1024, GP_E_SHAPE, "bad probe shape k=%d tp=%d", k, tp);
+  int64_t tot = p->row_count * tp;
+  probes_kernel<<<(unsigned)cdiv(tot, 256), 256, sizeof(float) * k * tp, p->stream>>>(Lt, k, p->n2, p->row_begin, p->row_count,
+                                                                                  eps1, eps2, tp, sqrtf(p->noise), Z);
+  p->launches++;
+  GP_CUDA(cudaGetLastError());
+  return GP_OK;
+}
