@@ -451,7 +451,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   for (kk = 0; kk < max_iter && !finished; ++kk) {
     status = kmv_partials(p, Pfull, done);
     if (status != GP_OK) break;
-    cg_finishv_kernel<<<G, CG_THREADS, 0, st>>>(p->partial.as<float>(), p->nsplit, rows_pad, p->outputscale, p->noise, P, V, n, red, done);
+    cg_finishv_kernel<<<G, CG_THREADS, 0, st>>>(p->partial.as<float>(), p->nparts, rows_pad, p->outputscale, p->noise, P, V, n, red, done);
     cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_a, done);
     if ((status = allreduce(p, sums_a, TP)) != GP_OK) break;
     cg_update_kernel<<<G, CG_THREADS, 0, st>>>(sums_a, kk, eps, P, V, U, R, n, S, red, L2);

@@ -124,6 +124,7 @@ struct gp_plan {
   int DP = 0;      // padded feature width of the SIMT arrays
   int KP = 0;      // padded augmented width (3d+4 -> multiple of 8) of the tcgen05 tiles
   int nsplit = 1;  // column splits of the K.V work (load balance over 148 SMs)
+  int nparts = 1;  // partial-sum slots written by the K.V kernel (nsplit, x2 for the tcgen05 kernel)
   int64_t ntile_i = 0, ntile_j = 0, tiles_per_split = 0;
   // device buffers
   gp::DevBuf mean, scale, Z1, Z2, XA, XB, V16, Vtiles, partial, out16;
@@ -159,7 +160,9 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// round-to-nearest (ties away) to tf32: the tensor core truncates fp32 containers to their top 19 bits,
+// so operands are pre-rounded and the 2-term split x = hi + lo is exact to ~2^-24 |x|.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // covariance from a = -0.5 |z_i - z_j|^2 in the pre-scaled units of pack.cu:
 //   RBF     z = (x - mean) sqrt(log2 e) / l      k = 2^a                (rbf_covariance.py:19)

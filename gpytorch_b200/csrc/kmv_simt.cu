@@ -132,7 +132,7 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
   int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
   int64_t tot = p->row_count * TP;
   float na = (add_noise && p->same) ? p->noise : 0.f;
-  kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nsplit, p->row_count,
+  kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count,
                                                                           rows_pad, p->outputscale, na, V16, p->row_begin,
                                                                           OUT, ldo, t);
   p->launches++;

@@ -12,12 +12,13 @@
 //                                      by pack.cu so that S_ij = -0.5|z_i - z_j|^2 directly), S in TMEM
 //   EPI    P  = cov(S)                 two epilogue warpgroups ping-pong: tcgen05.ld -> ex2/sqrt (MUFU) ->
 //                                      P_hi/P_lo (tf32 split) -> tcgen05.st back to TMEM (P_hi in place of S)
-//   GEMM2  O += P_hi V_hi + P_hi V_lo + P_lo V_hi      A operand from TMEM, B = V^T tile in smem, N=16
+//   GEMM2  O  = P_hi [V_hi;V_lo] (N=32) + P_lo V_hi (N=16)   A operand from TMEM, B = V^T tile in smem;
+//          O is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps
 // Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact
 // UMMA K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue WG0, 4-7 epilogue
 // WG1, 8 TMA producer, 9 TMEM allocator + MMA issuer.
 //
-// TMEM columns (512 allocated): [0,96) S0/P0hi  [96,192) P0lo  [192,288) S1/P1hi  [288,384) P1lo  [384,400) O
+// TMEM columns (512 allocated): [0,96) S0/P0hi  [96,192) P0lo  [192,288) S1/P1hi  [288,384) P1lo  [384,416) O0  [416,448) O1
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -26,9 +27,8 @@ namespace gp {
 using namespace ptx;
 
 constexpr int TC_THREADS = 320;
-constexpr int COL_S0 = 0, COL_PLO0 = 96, COL_STAGE = 192, COL_O = 384;
-constexpr int V_TILE_BYTES = 2 * TILE_J * TP * 4;  // hi + lo = 12288
-constexpr int V_HALF_BYTES = TILE_J * TP * 4;      // 6144
+constexpr int COL_S0 = 0, COL_PLO0 = 96, COL_STAGE = 192, COL_O = 384, COL_OSTAGE = 32;
+constexpr int V_TILE_BYTES = 2 * TILE_J * TP * 4;  // [96/4][32 rows: V_hi(16) | V_lo(16)][4] = 12288
 constexpr int MAX_NS = 4;
 
 struct TcBars {
@@ -37,7 +37,7 @@ struct TcBars {
   uint64_t b_empty[MAX_NS];
   uint64_t s_full[2];
   uint64_t p_full[2];
-  uint64_t o_full;
+  uint64_t o_full[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -49,7 +49,8 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
               int64_t rows_pad, int same, int64_t row_begin, const int* __restrict__ done_flag) {
   if (done_flag && *done_flag) return;  // CTA-uniform, before any barrier / TMEM state exists
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
   const int64_t it = blockIdx.x;
   const int split = blockIdx.y;
   const int64_t jt0 = (int64_t)split * tiles_per_split;
@@ -63,14 +64,6 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
   uint8_t* sStage = smem + a_bytes;
   TcBars* bars = reinterpret_cast<TcBars*>(smem + a_bytes + (size_t)NS * stage_bytes);
 
-  if (T == 0) {  // empty split (cannot happen with choose_geometry, kept for safety): zero the partial
-    if (threadIdx.x < TILE_I) {
-      float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + it * TILE_I + threadIdx.x) * TP);
-      for (int q = 0; q < 4; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return;
-  }
-
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->a_full), 1);
     for (int s = 0; s < MAX_NS; ++s) {
@@ -80,8 +73,8 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->s_full[s]), 1);
       mbar_init(smem_u32(&bars->p_full[s]), 128);
+      mbar_init(smem_u32(&bars->o_full[s]), 1);
     }
-    mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(smem_u32(&bars->tmem_base), 512);
@@ -91,13 +84,13 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0 && T > 0) {
       mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
       bulk_g2s(smem_u32(sA), XA + it * (int64_t)TILE_I * KP, a_bytes, smem_u32(&bars->a_full));
+      int sb = 0;
+      uint32_t par = 1;
       for (int u = 0; u < T; ++u) {
-        const int sb = u % NS;
-        const uint32_t par = ((u / NS) & 1) ^ 1;
         mbar_wait(smem_u32(&bars->b_empty[sb]), par);
         const uint32_t full = smem_u32(&bars->b_full[sb]);
         uint8_t* st = sStage + (size_t)sb * stage_bytes;
@@ -105,54 +98,51 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         mbar_arrive_expect_tx(full, stage_bytes);
         bulk_g2s(smem_u32(st), XB + jt * (int64_t)TILE_J * KP, b_bytes, full);
         bulk_g2s(smem_u32(st + b_bytes), Vt + jt * (int64_t)(2 * TILE_J * TP), V_TILE_BYTES, full);
+        if (++sb == NS) { sb = 0; par ^= 1; }
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);
-      constexpr uint32_t IDESC2 = idesc_tf32(TILE_I, TP);
+    // ===================== MMA issuer: the whole warp runs converged, one elected lane issues ==========
+    if (T > 0) {
+      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);   // S  = A B^T          128 x 96
+      constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);  // O += P_hi [V_hi;V_lo]^T  128 x 32
+      constexpr uint32_t IDESC2B = idesc_tf32(TILE_I, TP);      // O += P_lo V_hi^T         128 x 16
       const int ksteps1 = KP / 8;
-      const uint32_t a_addr = smem_u32(sA);
+      const uint64_t a_desc0 = smem_desc(smem_u32(sA), TILE_I * 16, 128);
       mbar_wait(smem_u32(&bars->a_full), 0);
-      uint32_t o_acc = 0;
+      int sb1 = 0, sb2 = 0;       // smem ring slots of GEMM1(u) and GEMM2(u-1)
+      uint32_t par1 = 0;
       for (int u = 0; u <= T; ++u) {
         if (u < T) {  // GEMM1(u): S[u&1] = A . B^T
-          const int sb = u % NS;
-          mbar_wait(smem_u32(&bars->b_full[sb]), (u / NS) & 1);
+          mbar_wait(smem_u32(&bars->b_full[sb1]), par1);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(sStage + (size_t)sb * stage_bytes);
+          const uint64_t b_desc0 = smem_desc(smem_u32(sStage + (size_t)sb1 * stage_bytes), TILE_J * 16, 128);
           const uint32_t d_s = tmem + (uint32_t)((u & 1) * COL_STAGE + COL_S0);
-          for (int ks = 0; ks < ksteps1; ++ks) {
-            uint64_t ad = smem_desc(a_addr + ks * (2 * TILE_I * 16), TILE_I * 16, 128);
-            uint64_t bd = smem_desc(b_addr + ks * (2 * TILE_J * 16), TILE_J * 16, 128);
-            mma_tf32_ss(d_s, ad, bd, IDESC1, ks > 0 ? 1u : 0u);
-          }
+          for (int ks = 0; ks < ksteps1; ++ks)
+            mma_tf32_ss(d_s, a_desc0 + (uint64_t)(ks * ((2 * TILE_I * 16) >> 4)), b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)),
+                        IDESC1, ks > 0 ? 1u : 0u);
           tc_commit(smem_u32(&bars->s_full[u & 1]));
+          if (++sb1 == NS) { sb1 = 0; par1 ^= 1; }
         }
-        if (u >= 1) {  // GEMM2(u-1): O += P . V
+        if (u >= 1) {  // GEMM2(u-1): O[v&1] = P . V   (fresh accumulator every tile, see epilogue)
           const int v = u - 1;
-          const int sb = v % NS;
           mbar_wait(smem_u32(&bars->p_full[v & 1]), (v >> 1) & 1);
           tc_fence_after();
-          const uint32_t v_addr = smem_u32(sStage + (size_t)sb * stage_bytes + b_bytes);
+          const uint64_t v_desc0 = smem_desc(smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes), 2 * TP * 16, 128);
           const uint32_t p_hi = tmem + (uint32_t)((v & 1) * COL_STAGE + COL_S0);
           const uint32_t p_lo = tmem + (uint32_t)((v & 1) * COL_STAGE + COL_PLO0);
-          const uint32_t d_o = tmem + COL_O;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t pa = (pass == 2) ? p_lo : p_hi;
-            const uint32_t vb = v_addr + ((pass == 1) ? V_HALF_BYTES : 0);
-            for (int ks = 0; ks < TILE_J / 8; ++ks) {
-              uint64_t bd = smem_desc(vb + ks * (2 * TP * 16), TP * 16, 128);
-              mma_tf32_ts(d_o, pa + ks * 8, bd, IDESC2, o_acc);
-              o_acc = 1;
-            }
-          }
-          tc_commit(smem_u32(&bars->b_empty[sb]));  // smem stage (B + V) and P[v&1] are free again
+          const uint32_t d_o = tmem + (uint32_t)(COL_O + (v & 1) * COL_OSTAGE);
+#pragma unroll
+          for (int ks = 0; ks < TILE_J / 8; ++ks)
+            mma_tf32_ts(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < TILE_J / 8; ++ks)
+            mma_tf32_ts(d_o, p_lo + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2B, 1u);
+          tc_commit(smem_u32(&bars->b_empty[sb2]));     // smem slot (B + V) and P[v&1] are free again
+          tc_commit(smem_u32(&bars->o_full[v & 1]));    // O[v&1] holds tile v's product
+          if (++sb2 == NS) sb2 = 0;
         }
       }
-      tc_commit(smem_u32(&bars->o_full));
     }
   } else {
     // ===================== epilogue warpgroups =====================
@@ -160,13 +150,20 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int64_t gi = row_begin + it * TILE_I + q * 32 + lane;  // global row of this thread
+    const uint32_t t_s = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_S0);
+    const uint32_t t_lo = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_PLO0);
+    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * COL_OSTAGE);
+    // O is flushed into fp32 registers after EVERY tile: the tensor core's accumulator truncates on each add,
+    // so long TMEM accumulation chains drift (1e-4 at N = 50k); 36 adds per tile keep it at ~1e-6.
+    float acc[TP];
+#pragma unroll
+    for (int c = 0; c < TP; ++c) acc[c] = 0.f;
+    int npend = 0;  // tiles whose O has not been folded into acc yet (0 or 1)
     for (int u = wg; u < T; u += 2) {
       mbar_wait(smem_u32(&bars->s_full[wg]), (u >> 1) & 1);
       tc_fence_after();
       const int64_t jbase = (jt0 + u) * TILE_J;
       const bool diag_tile = same && (row_begin + it * TILE_I < jbase + TILE_J) && (jbase < row_begin + (it + 1) * TILE_I);
-      const uint32_t t_s = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_S0);
-      const uint32_t t_lo = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_PLO0);
 #pragma unroll 1
       for (int ch = 0; ch < TILE_J / 32; ++ch) {
         uint32_t r[32], lo[32];
@@ -181,31 +178,42 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           float p = cov_from_arg<KIND>(__uint_as_float(r[c]));
-          uint32_t hi = __float_as_uint(p) & 0xFFFFE000u;
+          uint32_t hi = (__float_as_uint(p) + 0x1000u) & 0xFFFFE000u;  // RN to tf32
           lo[c] = __float_as_uint(p - __uint_as_float(hi));
           r[c] = hi;
         }
         GP_TMEM_ST32(t_s + ch * 32, r);
         GP_TMEM_ST32(t_lo + ch * 32, lo);
       }
+      if (npend) {  // fold the previous tile's O (GEMM2(u-2) finished long ago) before releasing P(u)
+        mbar_wait(smem_u32(&bars->o_full[wg]), ((u - 2) >> 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        GP_TMEM_LD32(t_o, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
+      }
+      npend = 1;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[wg]));
+      mbar_arrive(smem_u32(&bars->p_full[wg]));  // GEMM2(u) may now overwrite O[wg] and read P[wg]
     }
-    if (wg == 0) {
-      // final read-out of O for this (row tile, split)
-      mbar_wait(smem_u32(&bars->o_full), 0);
+    if (npend) {
+      const int ulast = wg + 2 * ((T - 1 - wg) / 2);
+      mbar_wait(smem_u32(&bars->o_full[wg]), (ulast >> 1) & 1);
       tc_fence_after();
-      uint32_t o[16];
-      GP_TMEM_LD16(tmem + lane_off + COL_O, o);
+      uint32_t o[32];
+      GP_TMEM_LD32(t_o, o);
       tmem_wait_ld();
-      const int64_t row = it * TILE_I + q * 32 + lane;
-      float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + row) * TP);
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
-        dst[qq] = make_float4(__uint_as_float(o[4 * qq]), __uint_as_float(o[4 * qq + 1]), __uint_as_float(o[4 * qq + 2]),
-                              __uint_as_float(o[4 * qq + 3]));
+      for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
     }
+    // each warpgroup owns one partial slot: partial[split * 2 + wg][row][16]
+    const int64_t row = it * TILE_I + q * 32 + lane;
+    float4* dst = reinterpret_cast<float4*>(partial + (((int64_t)split * 2 + wg) * rows_pad + row) * TP);
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
   }
   tc_fence_before();
   __syncthreads();

@@ -12,7 +12,7 @@
 //                                  [z_hi | z_lo | z_hi | n_hi n_lo 1 1 | 0..]   (3xTF32 split)
 //   XB   [ntile_j][KP/4][ 96][4]   B operand  [z_hi | z_hi | z_lo | 1 1 n_hi n_lo | 0..]
 //   so that  sum_k A_ik B_jk = z_i.z_j (to ~2^-22) + n_i + n_j,  n = -0.5 |z|^2  = a_ij.
-//   Vt   [ntile_j][2][96/4][16][4] hi / lo split of V^T tiles (B operand of GEMM2, K-major)
+//   Vt   [ntile_j][96/4][32][4]    V^T tiles, rows 0-15 = tf32 hi, rows 16-31 = tf32 lo (B operand of GEMM2)
 #include "gp_common.cuh"
 
 namespace gp {
@@ -57,7 +57,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ Z, int64_t row0, int64_
     for (int c = 0; c < d; ++c) nn += (double)z[c] * (double)z[c];
   nn *= -0.5;
   float n_hi = tf32_hi((float)nn);
-  float n_lo = (float)(nn - (double)n_hi);
+  float n_lo = tf32_hi((float)(nn - (double)n_hi));
   for (int kc = 0; kc < KP / 4; ++kc) {
     float v[4];
 #pragma unroll
@@ -69,7 +69,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ Z, int64_t row0, int64_
           int seg = kk / d, c = kk % d;
           float zz = z[c];
           float hi = tf32_hi(zz);
-          float lo = zz - hi;
+          float lo = tf32_hi(zz - hi);
           // A: hi lo hi ; B: hi hi lo
           bool want_lo = IS_A ? (seg == 1) : (seg == 2);
           val = want_lo ? lo : hi;
@@ -109,11 +109,11 @@ __global__ void pack_v_tiles_kernel(const float* __restrict__ V16, int64_t n2, i
     int64_t j = j0 + q;
     float v = (j < n2) ? V16[j * TP + c] : 0.f;
     hi[q] = tf32_hi(v);
-    lo[q] = v - hi[q];
+    lo[q] = tf32_hi(v - hi[q]);
   }
   float4* base = reinterpret_cast<float4*>(Vt + tile * (int64_t)(2 * TILE_J * TP));
-  base[kc * TP + c] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  base[(TILE_J / 4) * TP + kc * TP + c] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  base[kc * (2 * TP) + c] = make_float4(hi[0], hi[1], hi[2], hi[3]);        // B rows 0..15  = V_hi columns
+  base[kc * (2 * TP) + TP + c] = make_float4(lo[0], lo[1], lo[2], lo[3]);   // B rows 16..31 = V_lo columns
 }
 
 static int round_dp(int d) {
@@ -149,8 +149,8 @@ int choose_geometry(gp_plan* p) {
     double eff = (double)(nti * ntj) / (double)(waves * p->n_sm * per);
     if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
   }
-  p->nsplit = best;
   p->tiles_per_split = cdiv(ntj, best);
+  p->nsplit = (int)cdiv(ntj, p->tiles_per_split);  // no empty splits
   return GP_OK;
 }
 
@@ -201,7 +201,8 @@ int pack_inputs(gp_plan* p) {
     GP_CHECK(p->Vtiles.ensure(sizeof(float) * p->ntile_j * 2 * TILE_J * TP));
   }
   int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
-  GP_CHECK(p->partial.ensure(sizeof(float) * (size_t)p->nsplit * rows_pad * TP));
+  p->nparts = p->nsplit * (p->backend == GP_BACKEND_TCGEN05 ? 2 : 1);  // tcgen05: one slot per epilogue warpgroup
+  GP_CHECK(p->partial.ensure(sizeof(float) * (size_t)p->nparts * rows_pad * TP));
   GP_CUDA(cudaGetLastError());
   return GP_OK;
 }

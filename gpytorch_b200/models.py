@@ -1,0 +1,65 @@
+"""ExactGP (gpytorch/models/exact_gp.py:265-333) with the default prediction strategy's mean / covariance
+caches (models/exact_prediction_strategies.py:278-321, :371-478) on the engine's solve path."""
+import torch
+
+from . import settings
+from .distributions import MultivariateNormal
+from .likelihoods import GaussianLikelihood
+from .module import Module
+from .operators import KernelLinearOperator
+
+
+class ExactGP(Module):
+    def __init__(self, train_inputs, train_targets, likelihood):
+        if train_inputs is not None and torch.is_tensor(train_inputs):
+            train_inputs = (train_inputs,)
+        if not isinstance(likelihood, GaussianLikelihood):
+            raise RuntimeError("ExactGP can only handle Gaussian likelihoods")
+        super().__init__()
+        self.train_inputs = None if train_inputs is None else tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in train_inputs)
+        self.train_targets = train_targets
+        self.likelihood = likelihood
+        self._mean_cache = None
+
+    def train(self, mode=True):
+        if mode:
+            self._mean_cache = None  # module.py:351-355: train() clears caches
+        return super().train(mode)
+
+    def __call__(self, *args, **kwargs):
+        inputs = [a.unsqueeze(-1) if a.dim() == 1 else a for a in args]
+        if self.training:  # exact_gp.py:265-282
+            if self.train_inputs is None:
+                raise RuntimeError("train_inputs, train_targets cannot be None in training mode. "
+                                   "Call .eval() for prior predictions, or call .set_train_data() to add training data.")
+            if not all(torch.equal(ti, inp) for ti, inp in zip(self.train_inputs, inputs)):
+                raise RuntimeError("You must train on the training inputs!")
+            return self.forward(*inputs, **kwargs)
+        if self.train_inputs is None or self.train_targets is None:  # prior mode
+            return self.forward(*inputs, **kwargs)
+        # posterior mode (exact_gp.py:293-333, DefaultPredictionStrategy)
+        train_x, test_x = self.train_inputs[0], inputs[0]
+        train_out = self.forward(train_x)
+        with settings._use_eval_tolerance(True):
+            khat = self.likelihood(train_out).lazy_covariance_matrix
+            if self._mean_cache is None:
+                resid = (self.train_targets - train_out.mean).unsqueeze(-1)
+                self._mean_cache = khat.solve(resid).squeeze(-1)  # exact_prediction_strategies.py:286
+            kop = train_out.lazy_covariance_matrix
+            k_star = KernelLinearOperator(test_x.contiguous(), train_x, kop.kind, kop.lengthscale, kop.outputscale)
+            test_mean = self.mean_module(test_x) + k_star.matmul(self._mean_cache)  # :396
+            k_ss = KernelLinearOperator(test_x.contiguous(), None, kop.kind, kop.lengthscale, kop.outputscale)
+            k_xs = KernelLinearOperator(train_x, test_x.contiguous(), kop.kind, kop.lengthscale, kop.outputscale)
+            rhs = k_xs.to_dense()                    # [n, m]
+            corr = k_star.matmul(khat.solve(rhs))    # exact predictive covariance, :431-462
+            covar = k_ss.to_dense() - corr
+        return MultivariateNormal(test_mean, covar)
+
+    def set_train_data(self, inputs=None, targets=None, strict=True):
+        if inputs is not None:
+            if torch.is_tensor(inputs):
+                inputs = (inputs,)
+            self.train_inputs = tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in inputs)
+        if targets is not None:
+            self.train_targets = targets
+        self._mean_cache = None

@@ -1,0 +1,444 @@
+"""Engine-backed covariance operators: the LinearOperator duck-type subset the exact-GP path calls.
+
+Mirrors (reference paths under /root/reference/gpytorch):
+  * KernelLinearOperator returned by a kernel's forward, the KeOps plug-in pattern
+    (kernels/keops/rbf_kernel.py:44-55, keops/matern_kernel.py:68-80) -- `evaluate_kernel()` hands the
+    operator itself to the solver (lazy/lazy_evaluated_kernel_tensor.py:345-373);
+  * LazyEvaluatedKernelTensor hooks: _matmul (:245-276), _getitem (:136-243), _diagonal (:107-133),
+    _size (:277-318), _bilinear_derivative (:69-105);
+  * AddedDiagLinearOperator / InvQuadLogdet / solve of linear_operator,
+    reached from distributions/multivariate_normal.py:248-249 and
+    models/exact_prediction_strategies.py:286,444.
+
+All arithmetic runs in libgpbbmm (CUDA); torch supplies memory, streams and the autograd graph.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+
+from . import settings
+from ._lib import NumericalWarning
+from .engine import Plan
+
+
+def _as_list(ls: torch.Tensor):
+    return [float(v) for v in ls.detach().reshape(-1).tolist()]
+
+
+class ConstantDiagLinearOperator:
+    """sigma^2 I (likelihoods/noise_models.py:57-92 returns this for homoskedastic noise)."""
+
+    def __init__(self, diag_value: torch.Tensor, diag_shape: int):
+        self.diag_value = diag_value
+        self.n = int(diag_shape)
+
+    @property
+    def shape(self):
+        return torch.Size([self.n, self.n])
+
+    def to_dense(self):
+        return self.diag_value.reshape(()) * torch.eye(self.n, device=self.diag_value.device, dtype=self.diag_value.dtype)
+
+
+class KernelLinearOperator:
+    """K(x1, x2) (outputscale folded in) that never materialises: every product is the fused CUDA kernel."""
+
+    def __init__(self, x1, x2, kind, lengthscale, outputscale=None, plan: Plan | None = None, comm=None,
+                 row_begin=0, row_count=0):
+        self.x1, self.x2 = x1, x2
+        self.kind = kind
+        self.lengthscale = lengthscale          # tensor (scalar or [d]); may require grad
+        self.outputscale = outputscale if outputscale is not None else torch.ones((), device=x1.device)
+        self._plan = plan
+        self._comm = comm
+        self._row_begin, self._row_count = row_begin, row_count
+        self.same = x2 is None or x2 is x1 or (x1.shape == x2.shape and x1.data_ptr() == x2.data_ptr())
+
+    # -- plumbing --
+    def plan(self, noise: float = 0.0) -> Plan:
+        if self._plan is None:
+            self._plan = Plan(self.x1, None if self.same else self.x2, backend=settings.backend.value(),
+                              row_begin=self._row_begin, row_count=self._row_count, comm=self._comm)
+            self._hyp = None
+        key = (self.kind, tuple(_as_list(self.lengthscale)), float(self.outputscale), float(noise))
+        if getattr(self, "_hyp", None) != key:
+            self._plan.set_hypers(self.kind, _as_list(self.lengthscale), float(self.outputscale), float(noise))
+            self._hyp = key
+        return self._plan
+
+    @property
+    def shape(self):
+        n2 = self.x1.size(0) if self.same else self.x2.size(0)
+        return torch.Size([self.x1.size(0), n2])
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    @property
+    def dtype(self):
+        return self.x1.dtype
+
+    @property
+    def device(self):
+        return self.x1.device
+
+    @property
+    def batch_shape(self):
+        return torch.Size([])
+
+    @property
+    def requires_grad(self):
+        return bool(self.lengthscale.requires_grad or self.outputscale.requires_grad)
+
+    def evaluate_kernel(self):
+        return self  # "meta LinearOperator" branch, lazy_evaluated_kernel_tensor.py:345-348
+
+    def representation(self):
+        return (self.x1, self.x2, self.lengthscale, self.outputscale)
+
+    # -- products --
+    def matmul(self, rhs):
+        return _KernelMatmul.apply(self, rhs, self.lengthscale, self.outputscale)
+
+    __matmul__ = matmul
+    _matmul = matmul
+
+    def to_dense(self):
+        p = self.plan()
+        idx = torch.arange(self.x1.size(0), device=self.device)
+        return p.rows(idx)
+
+    def diagonal(self, dim1=-2, dim2=-1):
+        return self.plan().diag()
+
+    _diagonal = diagonal
+
+    def __getitem__(self, index):
+        """Row / column slicing by re-indexing x1 / x2 (lazy_evaluated_kernel_tensor.py:136-243)."""
+        if not isinstance(index, tuple):
+            index = (index, slice(None))
+        ri, ci = index
+        if isinstance(ri, int):
+            return self.plan().rows(torch.tensor([ri], device=self.device))[0][ci]
+        x1 = self.x1[ri]
+        x2 = (self.x1 if self.same else self.x2)[ci]
+        return KernelLinearOperator(x1, x2, self.kind, self.lengthscale, self.outputscale)
+
+    def __add__(self, other):
+        if isinstance(other, ConstantDiagLinearOperator):
+            return AddedDiagLinearOperator(self, other)
+        raise NotImplementedError("KernelLinearOperator only adds a ConstantDiagLinearOperator")
+
+    def add_jitter(self, jitter_val=1e-3):
+        return AddedDiagLinearOperator(self, ConstantDiagLinearOperator(torch.tensor(jitter_val, device=self.device), self.shape[0]))
+
+    def _bilinear_derivative(self, left, right):
+        """(d/d lengthscale, d/d outputscale) of sum(left * (K @ right)); lazy_evaluated_kernel_tensor.py:69-105."""
+        gl, go = self.plan(getattr(self, "_last_noise", 0.0)).bilinear_grad(left, right)
+        return torch.tensor(gl, device=self.device, dtype=self.dtype), torch.tensor(go, device=self.device, dtype=self.dtype)
+
+
+class _KernelMatmul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, op, rhs, lengthscale, outputscale):
+        ctx.op = op
+        out = op.plan(getattr(op, "_last_noise", 0.0)).kmv(rhs.detach())
+        ctx.save_for_backward(rhs.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        op = ctx.op
+        (rhs,) = ctx.saved_tensors
+        g = grad_out.contiguous()
+        vec = g.dim() == 1
+        g2 = g.unsqueeze(-1) if vec else g
+        r2 = rhs.unsqueeze(-1) if vec else rhs
+        grad_rhs = grad_ls = grad_os = None
+        if ctx.needs_input_grad[1]:
+            # K^T g: for x1 == x2 the operator is symmetric
+            if not op.same:
+                opT = KernelLinearOperator(op.x2, op.x1, op.kind, op.lengthscale, op.outputscale)
+                grad_rhs = opT.plan().kmv(g)
+            else:
+                grad_rhs = op.plan(getattr(op, "_last_noise", 0.0)).kmv(g)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            gl, go = op._bilinear_derivative(g2, r2)
+            grad_ls = gl.reshape(op.lengthscale.shape) if ctx.needs_input_grad[2] else None
+            grad_os = go.reshape(op.outputscale.shape) if ctx.needs_input_grad[3] else None
+        return None, grad_rhs, grad_ls, grad_os
+
+
+class AddedDiagLinearOperator:
+    """K + sigma^2 I with the BBMM solves (linear_operator AddedDiagLinearOperator, constant-diagonal case)."""
+
+    def __init__(self, kernel_op: KernelLinearOperator, diag: ConstantDiagLinearOperator):
+        if kernel_op.shape[0] != kernel_op.shape[1]:
+            raise RuntimeError("AddedDiagLinearOperator needs a square operator")
+        self.kernel_op = kernel_op
+        self.diag = diag
+        self._precond_cache = None
+
+    @property
+    def noise(self) -> torch.Tensor:
+        return self.diag.diag_value.reshape(())
+
+    @property
+    def shape(self):
+        return self.kernel_op.shape
+
+    def size(self, dim=None):
+        return self.kernel_op.size(dim)
+
+    @property
+    def dtype(self):
+        return self.kernel_op.dtype
+
+    @property
+    def device(self):
+        return self.kernel_op.device
+
+    @property
+    def batch_shape(self):
+        return torch.Size([])
+
+    def evaluate_kernel(self):
+        return self
+
+    def _plan(self) -> Plan:
+        self.kernel_op._last_noise = float(self.noise)
+        return self.kernel_op.plan(float(self.noise))
+
+    def matmul(self, rhs):
+        return self.kernel_op.matmul(rhs) + self.noise * rhs
+
+    __matmul__ = matmul
+
+    def to_dense(self):
+        return self.kernel_op.to_dense() + self.diag.to_dense()
+
+    def diagonal(self, dim1=-2, dim2=-1):
+        return self.kernel_op.diagonal() + self.noise
+
+    def add_jitter(self, jitter_val=1e-3):
+        return AddedDiagLinearOperator(self.kernel_op, ConstantDiagLinearOperator(self.noise + jitter_val, self.shape[0]))
+
+    # -- preconditioner (AddedDiagLinearOperator._preconditioner, Appendix A.4) --
+    def _preconditioner(self):
+        """Returns (W [n,k] | None, Lt [k,n] | None, logdet_P)."""
+        n = self.shape[0]
+        if settings.max_preconditioner_size.value() == 0 or n < settings.min_preconditioning_size.value():
+            return None, None, 0.0
+        if self._precond_cache is None:
+            p = self._plan()
+            lt, piv, st = p.pivoted_cholesky(settings.max_preconditioner_size.value(), settings.preconditioner_tolerance.value())
+            if st != 0 or lt.size(0) == 0:
+                self._precond_cache = (None, None, 0.0)
+            else:
+                w, logdet, st2 = p.precond_build(lt)
+                self._precond_cache = (None, None, 0.0) if st2 != 0 else (w, lt, logdet)
+        return self._precond_cache
+
+    def _probes(self, lt, tp):
+        n = self.shape[0]
+        seed = settings.probe_seed.value()
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        if lt is None:
+            z = torch.randint(0, 2, (n, tp), device=self.device, generator=gen).to(torch.float32) * 2 - 1
+            return z
+        eps1 = torch.randn(lt.size(0), tp, device=self.device, generator=gen)
+        eps2 = torch.randn(n, tp, device=self.device, generator=gen)
+        return self._plan().precond_probes(lt, eps1, eps2)
+
+    def _dense_cholesky(self):
+        return torch.linalg.cholesky(self.to_dense())
+
+    def solve(self, rhs, lhs=None):
+        """K_hat^{-1} rhs by preconditioned CG (LinearOperator.solve -> linear_cg, n_tridiag = 0)."""
+        out = _Solve.apply(self, rhs, self.kernel_op.lengthscale, self.kernel_op.outputscale, self.diag.diag_value)
+        return out if lhs is None else lhs @ out
+
+    def inv_quad_logdet(self, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True):
+        """(rhs^T K_hat^{-1} rhs, log det K_hat): distributions/multivariate_normal.py:249."""
+        if inv_quad_rhs is not None and inv_quad_rhs.size(0) != self.shape[0]:
+            raise RuntimeError(
+                f"LinearOperator (size={tuple(self.shape)}) cannot be multiplied with right-hand-side Tensor "
+                f"(size={tuple(inv_quad_rhs.shape)})")
+        rhs = inv_quad_rhs
+        if rhs is not None and rhs.dim() == 1:
+            rhs = rhs.unsqueeze(-1)
+        iq, ld = _InvQuadLogdet.apply(self, rhs, bool(logdet), self.kernel_op.lengthscale, self.kernel_op.outputscale,
+                                      self.diag.diag_value)
+        if rhs is None:
+            iq = torch.empty(0, device=self.device)
+        elif reduce_inv_quad:
+            iq = iq.sum(-1)
+        return iq, (ld if logdet else None)
+
+    def root_inv_decomposition(self, initial_vectors=None):
+        """Lanczos root of K_hat^{-1}: R with R R^T ~= K_hat^{-1} (exact_prediction_strategies.py:268-272)."""
+        p = self._plan()
+        n = self.shape[0]
+        init = initial_vectors if initial_vectors is not None else torch.randn(n, device=self.device)
+        if init.dim() == 2:
+            init = init[:, 0]
+        q, t = p.lanczos(init.float(), settings.max_root_decomposition_size.value())
+        evals, evecs = torch.linalg.eigh(t.double())
+        evals = evals.clamp_min(1e-12)
+        return (q.double() @ (evecs / evals.sqrt())).float()
+
+
+def _cg_tolerance():
+    return settings.eval_cg_tolerance.value() if settings._use_eval_tolerance.on() else settings.cg_tolerance.value()
+
+
+def _run_cg(op: AddedDiagLinearOperator, rhs, n_tridiag, w):
+    """linear_cg over <= 16 columns per call."""
+    p = op._plan()
+    outs, tmat, iters = [], None, 0
+    for c0 in range(0, rhs.size(1), 16):
+        blk = rhs[:, c0 : c0 + 16].contiguous()
+        nt = n_tridiag if c0 == 0 else 0
+        s, tm, info = p.mbcg(blk, nt, _cg_tolerance(), settings.max_cg_iterations.value(),
+                             settings.max_lanczos_quadrature_iterations.value(), w)
+        outs.append(s)
+        iters = max(iters, info.iters)
+        if nt:
+            tmat = tm
+    return (outs[0] if len(outs) == 1 else torch.cat(outs, -1)), tmat, iters
+
+
+class _Solve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, op, rhs, lengthscale, outputscale, noise):
+        vec = rhs.dim() == 1
+        r2 = (rhs.unsqueeze(-1) if vec else rhs).detach().float().contiguous()
+        n = op.shape[0]
+        if n <= settings.max_cholesky_size.value():
+            chol = op._dense_cholesky()
+            sol = torch.cholesky_solve(r2, chol)
+        else:
+            w, _, _ = op._preconditioner()
+            sol, _, _ = _run_cg(op, r2, 0, w)
+        ctx.op, ctx.vec = op, vec
+        ctx.save_for_backward(sol)
+        return sol.squeeze(-1) if vec else sol
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        op = ctx.op
+        (sol,) = ctx.saved_tensors
+        g = (grad_out.unsqueeze(-1) if ctx.vec else grad_out).contiguous()
+        n = op.shape[0]
+        if n <= settings.max_cholesky_size.value():
+            gsol = torch.cholesky_solve(g, op._dense_cholesky())
+        else:
+            w, _, _ = op._preconditioner()
+            gsol, _, _ = _run_cg(op, g, 0, w)
+        grad_rhs = (gsol.squeeze(-1) if ctx.vec else gsol) if ctx.needs_input_grad[1] else None
+        gl = go = gn = None
+        if any(ctx.needs_input_grad[2:]):
+            dls, dos = op.kernel_op._bilinear_derivative(-gsol, sol)
+            gl = dls.reshape(op.kernel_op.lengthscale.shape) if ctx.needs_input_grad[2] else None
+            go = dos.reshape(op.kernel_op.outputscale.shape) if ctx.needs_input_grad[3] else None
+            gn = (-(gsol * sol).sum()).reshape(op.diag.diag_value.shape) if ctx.needs_input_grad[4] else None
+        return None, grad_rhs, gl, go, gn
+
+
+class _InvQuadLogdet(torch.autograd.Function):
+    """linear_operator.functions._inv_quad_logdet.InvQuadLogdet."""
+
+    @staticmethod
+    def forward(ctx, op, rhs, want_logdet, lengthscale, outputscale, noise):
+        n = op.shape[0]
+        dev = op.device
+        ctx.op, ctx.want_logdet, ctx.has_rhs = op, want_logdet, rhs is not None
+        nr = 0 if rhs is None else rhs.size(1)
+        r = None if rhs is None else rhs.detach().float().contiguous()
+        if n <= settings.max_cholesky_size.value():  # the reference's dense branch (not the accelerated path)
+            chol = op._dense_cholesky()
+            sol = torch.cholesky_solve(r, chol) if r is not None else None
+            iq = (sol * r).sum(-2) if r is not None else torch.zeros(0, device=dev)
+            ld = 2 * chol.diagonal().log().sum() if want_logdet else torch.zeros((), device=dev)
+            ctx.mode = "chol"
+            ctx.save_for_backward(chol, sol if sol is not None else torch.zeros(0, device=dev))
+            return iq, ld
+        ctx.mode = "cg"
+        w, lt, logdet_p = op._preconditioner()
+        tp = settings.num_trace_samples.value() if (want_logdet or op.kernel_op.requires_grad or noise.requires_grad) else 0
+        cols = []
+        probes = None
+        if tp:
+            probes = op._probes(lt, tp)
+            norms = probes.norm(2, dim=-2, keepdim=True)
+            cols.append(probes / norms)
+        if r is not None:
+            cols.append(r)
+        full = torch.cat(cols, -1)
+        solves, tmat, iters = _run_cg(op, full, tp, w)
+        ld = torch.zeros((), device=dev)
+        if want_logdet and settings.skip_logdet_forward.off():
+            if torch.isnan(tmat).any():
+                ld = torch.tensor(float("nan"), device=dev)
+            else:
+                ld = torch.tensor(op._plan().slq_logdet(tmat, n) + logdet_p, device=dev, dtype=torch.float32)
+        iq = (solves[:, tp:] * r).sum(-2) if r is not None else torch.zeros(0, device=dev)
+        ctx.tp, ctx.iters = tp, iters
+        ctx.save_for_backward(solves, probes if probes is not None else torch.zeros(0, device=dev),
+                              w if w is not None else torch.zeros(0, device=dev))
+        op.last_cg_iters = iters
+        return iq, ld
+
+    @staticmethod
+    def backward(ctx, grad_iq, grad_ld):
+        op = ctx.op
+        gl = go = gn = grad_rhs = None
+        need_k = ctx.needs_input_grad[3] or ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        if ctx.mode == "chol":
+            chol, sol = ctx.saved_tensors
+            n = op.shape[0]
+            # dense: d iq = -sol sol^T : dK ; d logdet = K^-1 : dK
+            left_cols, right_cols = [], []
+            if ctx.has_rhs:
+                left_cols.append(-sol * grad_iq.reshape(1, -1)); right_cols.append(sol)
+                if ctx.needs_input_grad[1]:
+                    grad_rhs = 2 * sol * grad_iq.reshape(1, -1)
+            if need_k:
+                if ctx.want_logdet:
+                    kinv = torch.cholesky_inverse(chol)
+                    left_cols.append(kinv * grad_ld); right_cols.append(torch.eye(n, device=op.device))
+                left = torch.cat(left_cols, -1).contiguous(); right = torch.cat(right_cols, -1).contiguous()
+        else:
+            solves, probes, w = ctx.saved_tensors
+            tp = ctx.tp
+            left_cols, right_cols = [], []
+            if ctx.want_logdet and tp and need_k:
+                coef = 1.0 / tp
+                norms = probes.norm(2, dim=-2, keepdim=True)
+                pv_solves = solves[:, :tp] * coef * norms * grad_ld   # (1/tp) K^-1 z_i
+                pz = probes
+                if w.numel():
+                    pz = (probes - w @ (w.t() @ probes)) / op.noise.detach()  # P^-1 z_i
+                left_cols.append(pv_solves); right_cols.append(pz)
+            if ctx.has_rhs:
+                iq_solves = solves[:, tp:]
+                neg = -iq_solves * grad_iq.reshape(1, -1)
+                left_cols.append(neg); right_cols.append(iq_solves)
+                if ctx.needs_input_grad[1]:
+                    grad_rhs = -2 * neg
+            if need_k and left_cols:
+                left = torch.cat(left_cols, -1).contiguous(); right = torch.cat(right_cols, -1).contiguous()
+        if need_k and left_cols:
+            dls, dos = op.kernel_op._bilinear_derivative(left, right)
+            if ctx.needs_input_grad[3]:
+                gl = dls.reshape(op.kernel_op.lengthscale.shape)
+            if ctx.needs_input_grad[4]:
+                go = dos.reshape(op.kernel_op.outputscale.shape)
+            if ctx.needs_input_grad[5]:
+                gn = (left * right).sum().reshape(op.diag.diag_value.shape)
+        return None, grad_rhs, None, gl, go, gn

@@ -1,0 +1,90 @@
+"""world_size-2 gloo test (CPU) of the row-sharded mBCG message pattern used by csrc/cg.cu + csrc/comm.cu:
+per iteration one all-gather of the owned direction block and all-reduces of the packed dot products.
+The sharded run must reproduce the unsharded oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpytorch_b200.distributed import shard_rows
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _sharded_cg(rank, world, port, n, d, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import kernels as ok, linalg as ol, mll as om
+
+    x, y = om.synthetic_problem(n, d, 0, torch.float64)
+    b, c, per = shard_rows(n, world, rank)
+    assert c == per, "test uses n divisible by world"
+    Krows = ok.kernel_matrix("rbf", x, x, 0.25, 1.0, True)[b : b + c]  # this rank's row block of K
+    rhs_full = torch.randn(n, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(7))
+
+    # the sharded operator: local rows of (K + noise I) @ all-gathered V; dots are all-reduced
+    class ShardVec:
+        pass
+
+    def matmul_local(v_local):
+        parts = [torch.empty_like(v_local) for _ in range(world)]
+        dist.all_gather(parts, v_local.contiguous())
+        v_full = torch.cat(parts, 0)
+        return Krows @ v_full + 1.0 * v_local
+
+    # run the oracle CG on local rows with all-reduced reductions by monkey-patching sum/norm over dim -2
+    def allreduce_(t):
+        dist.all_reduce(t)
+        return t
+
+    rhs = rhs_full[b : b + c].clone()
+    # minimal re-statement of the iteration with explicit collectives (mirrors cg.cu's message schedule)
+    eps = 1e-10
+    nrm = allreduce_((rhs**2).sum(-2, keepdim=True)).sqrt()
+    rhs = rhs / nrm
+    R = rhs.clone(); U = torch.zeros_like(R); Z = R.clone(); P = Z.clone()
+    gamma = allreduce_((Z * R).sum(-2, keepdim=True))
+    for k in range(8):
+        V = matmul_local(P)
+        pv = allreduce_((P * V).sum(-2, keepdim=True))
+        alpha = torch.where(pv < eps, torch.zeros_like(pv), gamma / pv)
+        U += alpha * P; R -= alpha * V; Z = R.clone()
+        gnew = allreduce_((Z * R).sum(-2, keepdim=True))
+        beta = torch.where(gamma < eps, torch.zeros_like(gamma), gnew / gamma)
+        P = Z + beta * P; gamma = gnew
+    sol_local = U * nrm
+    parts = [torch.empty_like(sol_local) for _ in range(world)]
+    dist.all_gather(parts, sol_local)
+    if rank == 0:
+        A = ok.kernel_matrix("rbf", x, x, 0.25, 1.0, True) + 1.0 * torch.eye(n, dtype=torch.float64)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # fixed 8 iterations on both sides: "not converged" is expected
+            ref = ol.linear_cg(lambda v: A @ v, rhs_full, tolerance=1e-30, max_iter=8, max_tridiag_iter=8)
+        q.put(((torch.cat(parts, 0) - ref).norm() / ref.norm()).item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_row_sharded_cg_matches_unsharded_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_cg, args=(r, 2, port, 400, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=100)
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert err < 1e-9  # fp64 summation-order differences only

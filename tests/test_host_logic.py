@@ -1,0 +1,142 @@
+"""Host-side mirror of the reference interface: settings, constraints, kernel modules, error behaviour (CPU only)."""
+import math
+
+import pytest
+import torch
+
+import gpytorch_b200 as gp
+from gpytorch_b200 import settings
+from gpytorch_b200.constraints import GreaterThan, Positive, inv_softplus
+from gpytorch_b200.distributed import padded_size, shard_rows
+from gpytorch_b200.kernels import MaternKernel, RBFKernel, ScaleKernel
+
+
+def test_settings_defaults_match_reference():
+    # SURVEY.md Appendix A.1 (gpytorch/settings.py:6-31, :173-180)
+    assert settings.cg_tolerance.value() == 1.0
+    assert settings.eval_cg_tolerance.value() == 0.01
+    assert settings.max_cg_iterations.value() == 1000
+    assert settings.max_cholesky_size.value() == 800
+    assert settings.max_lanczos_quadrature_iterations.value() == 20
+    assert settings.max_preconditioner_size.value() == 15
+    assert settings.min_preconditioning_size.value() == 2000
+    assert settings.num_trace_samples.value() == 10
+    assert settings.preconditioner_tolerance.value() == 1e-3
+    assert settings.max_root_decomposition_size.value() == 100
+
+
+def test_settings_context_managers_nest_and_restore():
+    with settings.cg_tolerance(1e-4):
+        assert settings.cg_tolerance.value() == 1e-4
+        with settings.cg_tolerance(0.5), settings.max_preconditioner_size(100):
+            assert settings.cg_tolerance.value() == 0.5
+            assert settings.max_preconditioner_size.value() == 100
+        assert settings.cg_tolerance.value() == 1e-4
+    assert settings.cg_tolerance.value() == 1.0
+    assert settings.skip_logdet_forward.off()
+    with settings.skip_logdet_forward(True):
+        assert settings.skip_logdet_forward.on()
+    assert settings.skip_logdet_forward.off()
+
+
+def test_constraints_roundtrip():
+    v = torch.tensor([0.3, 1.0, 7.5])
+    assert torch.allclose(Positive().transform(Positive().inverse_transform(v)), v, atol=1e-6)
+    g = GreaterThan(1e-4)  # noise floor, likelihoods/noise_models.py:29-30
+    assert torch.all(g.transform(torch.tensor([-50.0, 0.0, 3.0])) >= 0.9999e-4)
+    assert torch.allclose(inv_softplus(torch.nn.functional.softplus(v)), v, atol=1e-6)
+
+
+def test_kernel_hyperparameters_and_initialize():
+    k = RBFKernel().initialize(lengthscale=2.0)
+    assert k.lengthscale.shape == (1, 1) and k.lengthscale.item() == pytest.approx(2.0, rel=1e-6)
+    k.lengthscale = 0.5
+    assert k.lengthscale.item() == pytest.approx(0.5, rel=1e-6)
+    ka = RBFKernel(ard_num_dims=3)
+    ka.lengthscale = torch.tensor([1.0, 2.0, 3.0])
+    assert torch.allclose(ka.lengthscale, torch.tensor([[1.0, 2.0, 3.0]]), atol=1e-6)
+    s = ScaleKernel(MaternKernel(nu=1.5)).initialize(outputscale=3.0)
+    assert s.outputscale.item() == pytest.approx(3.0, rel=1e-6)
+    assert s.base_kernel.kind == "matern32"
+    assert len(list(s.parameters())) == 2
+
+
+def test_matern_rejects_bad_nu():
+    with pytest.raises(RuntimeError, match="nu expected to be 0.5, 1.5, or 2.5"):  # matern_kernel.py:80-81
+        MaternKernel(nu=2.0)
+
+
+def test_kernel_call_contract_errors():
+    k = RBFKernel(ard_num_dims=3)
+    with pytest.raises(RuntimeError, match="ard_num_dims"):
+        k(torch.rand(5, 2))
+    k2 = RBFKernel()
+    with pytest.raises(RuntimeError, match="same number of dimensions"):  # kernels/kernel.py:506-507
+        k2(torch.rand(5, 2), torch.rand(4, 3))
+
+
+def test_kernel_forward_returns_lazy_operator_without_compute():
+    x = torch.rand(50, 4)
+    op = ScaleKernel(RBFKernel())(x)
+    assert tuple(op.shape) == (50, 50) and op.same and op.kind == "rbf"
+    assert op.evaluate_kernel() is op
+    op2 = RBFKernel()(x, torch.rand(7, 4))
+    assert tuple(op2.shape) == (50, 7) and not op2.same
+    sub = op[3:10, :]
+    assert tuple(sub.shape) == (7, 50)
+
+
+def test_ops_fail_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    op = RBFKernel()(torch.rand(20, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op.matmul(torch.rand(20, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gp.Plan(torch.rand(5, 2))
+
+
+def test_mll_module_type_checks():
+    lik = gp.likelihoods.GaussianLikelihood()
+    assert lik.noise.item() > 1e-4
+    lik.noise = 0.1
+    assert lik.noise.item() == pytest.approx(0.1, rel=1e-5)
+    with pytest.raises(RuntimeError, match="Gaussian"):
+        gp.mlls.ExactMarginalLogLikelihood(object(), None)
+
+
+def test_dense_log_prob_known_answer():
+    # /root/reference/test/distributions/test_multivariate_normal.py:23-43
+    mvn = gp.distributions.MultivariateNormal(torch.tensor([0.0, 1, 2]), torch.diag(torch.tensor([1.0, 0.75, 1.5])))
+    assert mvn.log_prob(torch.zeros(3)).item() == pytest.approx(-4.8157, abs=1e-4)
+
+
+def test_exact_gp_train_mode_guard():
+    class M(gp.models.ExactGP):
+        def __init__(self, x, y, lik):
+            super().__init__(x, y, lik)
+            self.mean_module = gp.means.ConstantMean()
+            self.covar_module = ScaleKernel(RBFKernel())
+
+        def forward(self, x):
+            return gp.distributions.MultivariateNormal(self.mean_module(x), self.covar_module(x))
+
+    x, y = torch.rand(10, 2), torch.rand(10)
+    m = M(x, y, gp.likelihoods.GaussianLikelihood())
+    m.train()
+    out = m(x)
+    assert tuple(out.lazy_covariance_matrix.shape) == (10, 10)
+    with pytest.raises(RuntimeError, match="You must train on the training inputs!"):  # exact_gp.py:276-280
+        m(torch.rand(10, 2))
+
+
+def test_shard_rows_cover_exactly():
+    for n, w in ((50000, 8), (200000, 8), (1001, 4), (7, 8)):
+        tot, prev_end = 0, 0
+        for r in range(w):
+            b, c, per = shard_rows(n, w, r)
+            assert b == prev_end or c == 0
+            prev_end = b + c
+            tot += c
+        assert tot == n
+        assert padded_size(n, w) % w == 0 and padded_size(n, w) >= n

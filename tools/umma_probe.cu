@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* Apk, const f
   const uint32_t a_bytes = K * M * 4, b_bytes = K * N1 * 4, v_bytes = N1 * N2 * 4;
   uint8_t* sA = smem; uint8_t* sB = sA + a_bytes; uint8_t* sV = sB + b_bytes;
   Bars* bars = reinterpret_cast<Bars*>(sV + v_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_idx_uniform(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->full), 1); mbar_init(smem_u32(&bars->mma1), 1);
     mbar_init(smem_u32(&bars->pfull), 128); mbar_init(smem_u32(&bars->mma2), 1);
@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* Apk, const f
     bulk_g2s(smem_u32(sA), Apk, a_bytes, smem_u32(&bars->full));
     bulk_g2s(smem_u32(sB), Bpk, b_bytes, smem_u32(&bars->full));
     bulk_g2s(smem_u32(sV), Vpk, v_bytes, smem_u32(&bars->full));
+  }
+  if (warp == 0) {  // converged warp, elected lane issues (same pattern as kmv_tc.cu)
     mbar_wait(smem_u32(&bars->full), 0);
     tc_fence_after();
     for (int ks = 0; ks < K / 8; ++ks) {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* Apk, const f
   tmem_wait_st();
   tc_fence_before();
   mbar_arrive(smem_u32(&bars->pfull));
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     mbar_wait(smem_u32(&bars->pfull), 0);
     tc_fence_after();
     for (int ks = 0; ks < N1 / 8; ++ks) {
