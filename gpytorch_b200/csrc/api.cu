@@ -194,6 +194,32 @@ extern "C" int gp_plan_info(gp_plan* p, int* backend, int* nsplit, int* kpad, in
   return GP_OK;
 }
 
+extern "C" int gp_time_kmv_kernel(gp_plan* p, const float* V, int64_t ldv, int t, int warmup, int reps, float* ms_per_launch) {
+  GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(t >= 1 && t <= TP && reps >= 1 && ms_per_launch, GP_E_SHAPE, "bad timing arguments");
+  GP_CUDA(cudaSetDevice(p->device));
+  GP_CHECK(p->V16.ensure(sizeof(float) * p->n2 * TP));
+  GP_CHECK(to_v16(p, V, ldv, t, p->n2, p->V16.as<float>()));
+  if (p->backend == GP_BACKEND_TCGEN05) GP_CHECK(pack_v_tiles(p, p->V16.as<float>()));
+  auto launch = [&]() -> int {
+    return p->backend == GP_BACKEND_TCGEN05 ? kmv_tc_launch(p, nullptr) : kmv_simt_launch(p, p->V16.as<float>(), nullptr);
+  };
+  for (int i = 0; i < warmup; ++i) GP_CHECK(launch());
+  cudaEvent_t e0, e1;
+  GP_CUDA(cudaEventCreate(&e0));
+  GP_CUDA(cudaEventCreate(&e1));
+  GP_CUDA(cudaEventRecord(e0, p->stream));
+  for (int i = 0; i < reps; ++i) GP_CHECK(launch());
+  GP_CUDA(cudaEventRecord(e1, p->stream));
+  GP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  GP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
+  return GP_OK;
+}
+
 // MultivariateNormal.log_prob through inv_quad_logdet (distributions/multivariate_normal.py:248-251)
 extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, const float* eps2, const float* rademacher,
                       const gp_mll_opts* o, float* solve_out, gp_mll_result* res) {

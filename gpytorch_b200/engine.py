@@ -92,6 +92,13 @@ class Plan:
         check(self.lib.gp_plan_info(self._h, C.byref(b), C.byref(s), C.byref(k), C.byref(m)))
         return {"backend": {1: "tcgen05", 2: "simt"}.get(b.value, "?"), "nsplit": s.value, "kpad": k.value, "n_sm": m.value}
 
+    def time_kmv_kernel(self, v: torch.Tensor, warmup: int = 3, reps: int = 20) -> float:
+        """Average device time (ms) of ONE launch of the fused K.V kernel alone (CUDA events on the plan stream)."""
+        v = v.contiguous()
+        ms = C.c_float()
+        check(self.lib.gp_time_kmv_kernel(self._h, _ptr(v), v.stride(0), v.size(1), warmup, reps, C.byref(ms)))
+        return ms.value
+
     def launches(self) -> int:
         return int(self.lib.gp_kernel_launches(self._h))
 

@@ -28,6 +28,31 @@ def _as_list(ls: torch.Tensor):
     return [float(v) for v in ls.detach().reshape(-1).tolist()]
 
 
+# Plans own device workspaces (packed tiles, CG vectors); re-use them across operators over the same buffers so a
+# training loop does not re-allocate every step.  Hyper-parameters / data are re-packed whenever a new operator
+# first touches a cached plan.
+_PLAN_CACHE: "dict[tuple, Plan]" = {}
+_PLAN_CACHE_MAX = 6
+
+
+def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
+    key = (x1.data_ptr(), tuple(x1.shape), x1.stride(0), None if x2 is None else (x2.data_ptr(), tuple(x2.shape), x2.stride(0)),
+           backend, str(x1.device), row_begin, row_count, id(comm))
+    plan = _PLAN_CACHE.pop(key, None)
+    if plan is None:
+        plan = Plan(x1, x2, backend=backend, row_begin=row_begin, row_count=row_count, comm=comm)
+        plan._hyp_key = None
+    _PLAN_CACHE[key] = plan  # most recently used last
+    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+    return plan
+
+
+def clear_plan_cache():
+    while _PLAN_CACHE:
+        _PLAN_CACHE.popitem()[1].close()
+
+
 class ConstantDiagLinearOperator:
     """sigma^2 I (likelihoods/noise_models.py:57-92 returns this for homoskedastic noise)."""
 
@@ -59,14 +84,15 @@ class KernelLinearOperator:
 
     # -- plumbing --
     def plan(self, noise: float = 0.0) -> Plan:
+        fresh = False
         if self._plan is None:
-            self._plan = Plan(self.x1, None if self.same else self.x2, backend=settings.backend.value(),
-                              row_begin=self._row_begin, row_count=self._row_count, comm=self._comm)
-            self._hyp = None
+            self._plan = _get_plan(self.x1, None if self.same else self.x2, settings.backend.value(),
+                                   self._row_begin, self._row_count, self._comm)
+            fresh = True
         key = (self.kind, tuple(_as_list(self.lengthscale)), float(self.outputscale), float(noise))
-        if getattr(self, "_hyp", None) != key:
+        if fresh or getattr(self._plan, "_hyp_key", None) != key:
             self._plan.set_hypers(self.kind, _as_list(self.lengthscale), float(self.outputscale), float(noise))
-            self._hyp = key
+            self._plan._hyp_key = key
         return self._plan
 
     @property

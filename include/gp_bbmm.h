@@ -168,6 +168,9 @@ int gp_plan_set_comm(gp_plan* plan, gp_comm* comm);      /* NULL = single GPU */
 /* ---- introspection for bench.py --------------------------------------------------- */
 int64_t gp_kernel_launches(gp_plan* plan);               /* kernels launched by this plan so far */
 int gp_plan_info(gp_plan* plan, int* backend, int* nsplit, int* kpad, int* n_sm);
+/* Times `reps` back-to-back launches of the fused K.V kernel ALONE (after `warmup` untimed ones) with CUDA
+ * events on the plan's stream; V [n2, t].  *ms_per_launch is the average device time of one launch. */
+int gp_time_kmv_kernel(gp_plan* plan, const float* V, int64_t ldv, int t, int warmup, int reps, float* ms_per_launch);
 
 #ifdef __cplusplus
 }
