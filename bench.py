@@ -117,7 +117,7 @@ def cpu_reference_eval(w, n_sample, seed=0):
     return time.perf_counter() - t0, r
 
 
-def cpu_baseline(w, budget_rows=20000):
+def cpu_baseline(w, budget_rows=12500):
     import torch
 
     cores = os.cpu_count() or 1
@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GP_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--backend", default="auto", choices=["auto", "tcgen05", "simt"])
-    ap.add_argument("--ref-rows", type=int, default=20000, help="rows of the bounded CPU sample")
+    ap.add_argument("--ref-rows", type=int, default=12500, help="rows of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -38,14 +38,23 @@ __device__ __forceinline__ void block_reduce_cols(float4 acc, float* red /*[CG_R
   if (tid < TP) out[tid] = red[tid];
 }
 
-// sum G partial vectors of length L (fp32) into fp64, fixed order
+// sum G partial vectors of length L (fp32) into fp64, fixed order.  Block = 32 outputs x 8 partial groups.
 __global__ void cg_sum_kernel(const float* __restrict__ in, int G, int L, double* __restrict__ out, const int* done) {
   if (done && *done) return;
-  int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= L) return;
+  __shared__ double sh[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int b = 0; b < G; ++b) s += (double)in[(size_t)b * L + o];
-  out[o] = s;
+  if (o < L)
+    for (int b = grp; b < G; b += 8) s += (double)in[(size_t)b * L + o];
+  sh[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && o < L) {
+    double t = 0.0;
+#pragma unroll
+    for (int g2 = 0; g2 < 8; ++g2) t += sh[g2][lane];
+    out[o] = t;
+  }
 }
 
 __global__ void cg_rhs_sq_kernel(const float* __restrict__ RHS, int64_t ldr, int t, int64_t n, float* __restrict__ part) {
@@ -381,7 +390,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   const float eps = 1e-10f, stop_after = 1e-10f;
   const int n_tridiag_iter = (int)std::min<int64_t>(max_tridiag_iter, N);
   const bool precond = W != nullptr;
-  const int G = (int)std::min<int64_t>(cdiv(n, CG_ROWS), 4 * p->n_sm);
+  const int G = (int)std::min<int64_t>(cdiv(n, CG_ROWS), 2 * p->n_sm);
   const int L2 = TP + (precond ? k * TP : 0);  // length of the second reduction message (rr | QtR)
 
   GP_CHECK(p->cgU.ensure(sizeof(float) * n * TP));
@@ -416,20 +425,20 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
 
   // ---- init: normalise rhs, R, U, Z = M^-1 R, P = Z, gamma ----
   cg_rhs_sq_kernel<<<G, CG_THREADS, 0, st>>>(RHS, ldr, t, n, red);
-  cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_a, nullptr);
+  cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_a, nullptr);
   GP_CHECK(allreduce(p, sums_a, TP));
   cg_init_kernel<<<G, CG_THREADS, 0, st>>>(RHS, ldr, t, n, sums_a, eps, U, R, S, red);
   p->launches += 3;
   if (precond) {
     cg_qtr_kernel<<<G, CG_THREADS, sh_qtr, st>>>(W, k, R, n, red, L2, TP, nullptr);
-    cg_sum_kernel<<<(unsigned)cdiv(L2, 128), 128, 0, st>>>(red, G, L2, sums_b, nullptr);
+    cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 256, 0, st>>>(red, G, L2, sums_b, nullptr);
     GP_CHECK(allreduce(p, sums_b, L2));
     cg_precond_kernel<<<G, CG_THREADS, sh_pre, st>>>(W, k, sums_b + TP, inv_noise, R, Z, n, red, nullptr);
-    cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_zr, nullptr);
+    cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_zr, nullptr);
     GP_CHECK(allreduce(p, sums_zr, TP));
     p->launches += 4;
   } else {
-    cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_zr, nullptr);  // Z = R: gamma = sum R^2 (partials of cg_init)
+    cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_zr, nullptr);  // Z = R: gamma = sum R^2 (partials of cg_init)
     GP_CHECK(allreduce(p, sums_zr, TP));
     p->launches += 1;
   }
@@ -452,20 +461,20 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
     status = kmv_partials(p, Pfull, done);
     if (status != GP_OK) break;
     cg_finishv_kernel<<<G, CG_THREADS, 0, st>>>(p->partial.as<float>(), p->nparts, rows_pad, p->outputscale, p->noise, P, V, n, red, done);
-    cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_a, done);
+    cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_a, done);
     if ((status = allreduce(p, sums_a, TP)) != GP_OK) break;
     cg_update_kernel<<<G, CG_THREADS, 0, st>>>(sums_a, kk, eps, P, V, U, R, n, S, red, L2);
     p->launches += 3;
     if (precond) {
       cg_qtr_kernel<<<G, CG_THREADS, sh_qtr, st>>>(W, k, R, n, red, L2, TP, done);
-      cg_sum_kernel<<<(unsigned)cdiv(L2, 128), 128, 0, st>>>(red, G, L2, sums_b, done);
+      cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 256, 0, st>>>(red, G, L2, sums_b, done);
       if ((status = allreduce(p, sums_b, L2)) != GP_OK) break;
       cg_precond_kernel<<<G, CG_THREADS, sh_pre, st>>>(W, k, sums_b + TP, inv_noise, R, Z, n, red, done);
-      cg_sum_kernel<<<1, 128, 0, st>>>(red, G, TP, sums_zr, done);
+      cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_zr, done);
       if ((status = allreduce(p, sums_zr, TP)) != GP_OK) break;
       p->launches += 4;
     } else {
-      cg_sum_kernel<<<1, 128, 0, st>>>(red, G, L2, sums_b, done);
+      cg_sum_kernel<<<1, 256, 0, st>>>(red, G, L2, sums_b, done);
       if ((status = allreduce(p, sums_b, TP)) != GP_OK) break;
       p->launches += 1;
     }

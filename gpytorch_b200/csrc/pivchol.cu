@@ -13,42 +13,72 @@
 namespace gp {
 
 struct PcState {
-  int done;        // stop rule fired (error <= tol) -> later launches are no-ops
+  int done;        // stop rule fired (error <= tol, or NaN) -> later launches are no-ops
   int rank;        // steps completed
-  int pivot;       // current pivot (global row)
+  int pivot;       // pivot (global row) selected for the NEXT step to run
   int nan_flag;
   float dpiv;      // sqrt(max diag) = L[m][pivot]
   float orig_err;  // max of the initial diagonal
   float err;
+  unsigned int counter;  // last-block-done ticket
 };
 
-constexpr int PC_SEL_THREADS = 1024;
+constexpr int PC_THREADS = 256;
 
-// single CTA: error check + argmax over the not-yet-pivoted entries + permutation swap
-__global__ void __launch_bounds__(PC_SEL_THREADS)
-pc_select_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, int m, float tol,
-                 PcState* __restrict__ st, int64_t* __restrict__ piv_out) {
+// One launch per step m, fused: row update with the pivot chosen by the previous launch,
+// then -- in the same pass -- the per-CTA (max, earliest permutation position, sum |diag|) over the remaining
+// entries; the last CTA to finish reduces the partials, applies the stop rule and selects / swaps the next pivot.
+//   L[m][j] = (K[pi, j] - sum_{q<m} L[q][pi] L[q][j]) / L[m][pi] ; diag[j] -= L[m][j]^2
+template <int KIND>
+__global__ void __launch_bounds__(PC_THREADS)
+pc_step_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict__ Lt, int64_t n, int m, int max_rank,
+               float tol, float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, PcState* __restrict__ st,
+               int64_t* __restrict__ piv_out, float* __restrict__ pval, int* __restrict__ ppos, double* __restrict__ psum) {
   if (st->done) return;
-  __shared__ float s_val[PC_SEL_THREADS];
-  __shared__ int s_pos[PC_SEL_THREADS];
-  __shared__ double s_sum[PC_SEL_THREADS];
+  extern __shared__ float sh[];
+  float* zp = sh;           // [DP]
+  float* lp = sh + DP;      // [m]   L[q][pivot]
+  __shared__ float s_val[PC_THREADS];
+  __shared__ int s_pos[PC_THREADS];
+  __shared__ double s_sum[PC_THREADS];
+  __shared__ bool s_last;
   const int tid = threadIdx.x;
+  const int pi = st->pivot;
+  const float dpiv = st->dpiv;
+  for (int c = tid; c < DP; c += PC_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+  for (int q = tid; q < m; q += PC_THREADS) lp[q] = Lt[(int64_t)q * n + pi];
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * PC_THREADS + tid;
   float best = -INFINITY;
   int best_pos = 0x7fffffff;
   double asum = 0.0;
-  bool nan_seen = false;
-  for (int64_t j = tid; j < n; j += PC_SEL_THREADS) {
-    int pj = pos[j];
-    if (pj < m) continue;  // already a pivot
-    float v = diag[j];
-    if (v != v) nan_seen = true;
-    asum += fabs((double)v);
-    if (v > best || (v == best && pj < best_pos)) { best = v; best_pos = pj; }
+  if (j < n) {
+    float* Lm = Lt + (int64_t)m * n;
+    const int pj = pos[j];
+    if (pj < m) {
+      Lm[j] = 0.f;               // earlier pivots stay zero in this row
+    } else if (pj == m) {
+      Lm[j] = dpiv;              // the pivot itself
+    } else {
+      float s = 0.f;
+      for (int c = 0; c < DP; ++c) {
+        float df = zp[c] - Z[j * DP + c];
+        s = fmaf(df, df, s);
+      }
+      float v = os * cov_from_arg<KIND>(-0.5f * s);
+      for (int q = 0; q < m; ++q) v = fmaf(-lp[q], Lt[(int64_t)q * n + j], v);
+      v /= dpiv;
+      Lm[j] = v;
+      float dn = diag[j] - v * v;
+      diag[j] = dn;
+      if (dn != dn) { best = INFINITY; best_pos = -1; }  // NaN poisons the selection
+      else { best = dn; best_pos = pj; }
+      asum = fabs((double)dn);
+    }
   }
-  if (nan_seen) { best = INFINITY; best_pos = -1; }
   s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
   __syncthreads();
-  for (int s = PC_SEL_THREADS / 2; s > 0; s >>= 1) {
+  for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
     if (tid < s) {
       float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
       if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
@@ -57,69 +87,65 @@ pc_select_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restri
     __syncthreads();
   }
   if (tid == 0) {
-    float mx = s_val[0];
-    int pp = s_pos[0];
-    if (pp < 0 || !(mx > 0.f)) {  // NaN or non-positive pivot: the reference ends up with NaNs in L
+    pval[blockIdx.x] = s_val[0]; ppos[blockIdx.x] = s_pos[0]; psum[blockIdx.x] = s_sum[0];
+    __threadfence();
+    unsigned int ticket = atomicAdd(&st->counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA: fixed-order reduction of the partials, stop rule, next pivot ----
+  best = -INFINITY; best_pos = 0x7fffffff; asum = 0.0;
+  for (int b = tid; b < (int)gridDim.x; b += PC_THREADS) {
+    float v2 = ((volatile float*)pval)[b]; int p2 = ((volatile int*)ppos)[b];
+    if (v2 > best || (v2 == best && p2 < best_pos)) { best = v2; best_pos = p2; }
+  }
+  s_val[tid] = best; s_pos[tid] = best_pos;
+  __syncthreads();
+  for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
+      if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) tot += ((volatile double*)psum)[b];
+    st->counter = 0;
+    st->rank = m + 1;
+    const float err = (float)(tot / (double)st->orig_err);
+    st->err = err;
+    const float mx = s_val[0];
+    const int pp = s_pos[0];
+    // while (m == 0) or (m < max_iter and max(errors) > error_tol): will step m+1 run?
+    if (m + 1 >= max_rank || (int64_t)(m + 1) >= n || !(err > tol)) {
+      st->done = 1;
+    } else if (pp < 0 || !(mx > 0.f)) {  // NaN / non-positive pivot: the reference ends up with NaNs in L
       st->nan_flag = 1;
       st->done = 1;
-      st->rank = m;
-      return;
+    } else {
+      const int pi_new = perm[pp];
+      const int pi_old = perm[m + 1];
+      perm[m + 1] = pi_new; perm[pp] = pi_old;
+      pos[pi_new] = m + 1; pos[pi_old] = pp;
+      st->pivot = pi_new;
+      st->dpiv = sqrtf(mx);
+      piv_out[m + 1] = (int64_t)pi_new;
     }
-    if (m == 0) st->orig_err = mx;
-    float err = (float)(s_sum[0] / (double)st->orig_err);
-    st->err = err;
-    if (m > 0 && !(err > tol)) {  // while (m == 0) or (m < max_iter and max(errors) > error_tol)
-      st->done = 1;
-      st->rank = m;
-      return;
-    }
-    // swap perm[m] <-> perm[pp]
-    int pi_new = perm[pp];
-    int pi_old = perm[m];
-    perm[m] = pi_new; perm[pp] = pi_old;
-    pos[pi_new] = m; pos[pi_old] = pp;
-    st->pivot = pi_new;
-    st->dpiv = sqrtf(mx);
-    st->rank = m + 1;
-    piv_out[m] = (int64_t)pi_new;
   }
-}
-
-// row update: L[m][j] = (K[pi, j] - sum_{q<m} L[q][pi] L[q][j]) / L[m][pi] ; diag[j] -= L[m][j]^2
-template <int KIND>
-__global__ void pc_update_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict__ Lt, int64_t n, int m,
-                                 float* __restrict__ diag, const int* __restrict__ pos, const PcState* __restrict__ st) {
-  if (st->done) return;
-  extern __shared__ float sh[];
-  float* zp = sh;           // [DP]
-  float* lp = sh + DP;      // [m]   L[q][pivot]
-  const int pi = st->pivot;
-  const float dpiv = st->dpiv;
-  for (int c = threadIdx.x; c < DP; c += blockDim.x) zp[c] = Z[(int64_t)pi * DP + c];
-  for (int q = threadIdx.x; q < m; q += blockDim.x) lp[q] = Lt[(int64_t)q * n + pi];
-  __syncthreads();
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  float* Lm = Lt + (int64_t)m * n;
-  const int pj = pos[j];
-  if (pj < m) { Lm[j] = 0.f; return; }       // earlier pivots stay zero in this row
-  if (pj == m) { Lm[j] = dpiv; return; }     // the pivot itself
-  float s = 0.f;
-  for (int c = 0; c < DP; ++c) {
-    float df = zp[c] - Z[j * DP + c];
-    s = fmaf(df, df, s);
-  }
-  float v = os * cov_from_arg<KIND>(-0.5f * s);
-  for (int q = 0; q < m; ++q) v = fmaf(-lp[q], Lt[(int64_t)q * n + j], v);
-  v /= dpiv;
-  Lm[j] = v;
-  diag[j] -= v * v;
 }
 
 __global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, float os,
-                               PcState* __restrict__ st) {
+                               PcState* __restrict__ st, int64_t* __restrict__ piv_out) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) { st->done = 0; st->rank = 0; st->pivot = 0; st->nan_flag = 0; st->dpiv = 0.f; st->orig_err = 1.f; st->err = 0.f; }
+  if (j == 0) {
+    // the initial diagonal of a stationary kernel is constant: torch.max returns the first entry -> pivot 0
+    st->done = 0; st->rank = 0; st->pivot = 0; st->nan_flag = (os > 0.f) ? 0 : 1; st->dpiv = sqrtf(os);
+    st->orig_err = os; st->err = 0.f; st->counter = 0u;
+    piv_out[0] = 0;
+  }
   if (j >= n) return;
   diag[j] = os;  // _approx_diagonal of a stationary kernel
   perm[j] = (int)j;
@@ -233,30 +259,34 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
   rank = (int)std::min<int64_t>(rank, n);
   GP_REQUIRE(rank >= 1, GP_E_SHAPE, "rank must be >= 1");
   cudaStream_t st = p->stream;
+  const unsigned gb = (unsigned)cdiv(n, PC_THREADS);
   GP_CHECK(p->pcdiag.ensure(sizeof(float) * n));
   GP_CHECK(p->pcperm.ensure(sizeof(int) * n));
   GP_CHECK(p->pcpos.ensure(sizeof(int) * n));
-  GP_CHECK(p->pcstate.ensure(sizeof(PcState)));
+  GP_CHECK(p->pcstate.ensure(sizeof(PcState) + 256 + (sizeof(float) + sizeof(int) + sizeof(double)) * gb + 64));
   float* diag = p->pcdiag.as<float>();
   int* perm = p->pcperm.as<int>();
   int* pos = p->pcpos.as<int>();
   PcState* S = p->pcstate.as<PcState>();
-  const unsigned gb = (unsigned)cdiv(n, 256);
-  pc_init_kernel<<<gb, 256, 0, st>>>(diag, perm, pos, n, p->outputscale, S);
+  double* psum = reinterpret_cast<double*>(reinterpret_cast<char*>(S) + 256);
+  float* pval = reinterpret_cast<float*>(psum + gb);
+  int* ppos = reinterpret_cast<int*>(pval + gb);
   GP_CUDA(cudaMemsetAsync(Lt, 0, sizeof(float) * (size_t)rank * n, st));
   GP_CUDA(cudaMemsetAsync(piv, 0, sizeof(int64_t) * rank, st));
+  pc_init_kernel<<<gb, PC_THREADS, 0, st>>>(diag, perm, pos, n, p->outputscale, S, piv);
   p->launches += 1;
   const float* Z = p->Z2.as<float>();
   for (int m = 0; m < rank; ++m) {
-    pc_select_kernel<<<1, PC_SEL_THREADS, 0, st>>>(diag, perm, pos, n, m, error_tol, S, piv);
     size_t sh = sizeof(float) * (p->DP + m);
+#define GP_PC_LAUNCH(KK) pc_step_kernel<KK><<<gb, PC_THREADS, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, rank, error_tol, diag, perm, pos, S, piv, pval, ppos, psum)
     switch (p->kind) {
-      case GP_RBF: pc_update_kernel<GP_RBF><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
-      case GP_MATERN12: pc_update_kernel<GP_MATERN12><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
-      case GP_MATERN32: pc_update_kernel<GP_MATERN32><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
-      default: pc_update_kernel<GP_MATERN52><<<gb, 256, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, diag, pos, S); break;
+      case GP_RBF: GP_PC_LAUNCH(GP_RBF); break;
+      case GP_MATERN12: GP_PC_LAUNCH(GP_MATERN12); break;
+      case GP_MATERN32: GP_PC_LAUNCH(GP_MATERN32); break;
+      default: GP_PC_LAUNCH(GP_MATERN52); break;
     }
-    p->launches += 2;
+#undef GP_PC_LAUNCH
+    p->launches += 1;
   }
   GP_CUDA(cudaGetLastError());
   PcState* hs = reinterpret_cast<PcState*>(reinterpret_cast<char*>(p->pinned) + 2048);

@@ -168,8 +168,8 @@ class Plan:
         rhs = rhs.contiguous()
         n, t = rhs.shape
         solves = torch.empty_like(rhs)
-        mti = min(max_tridiag_iter, max_iter)
-        tmat = torch.zeros(max(n_tridiag, 1), mti, mti, device=self.device, dtype=torch.float32)
+        mti = int(max_tridiag_iter)  # > max_iter is rejected by the engine like the reference does
+        tmat = torch.zeros(max(n_tridiag, 1), min(mti, 4096), min(mti, 4096), device=self.device, dtype=torch.float32)
         it, js = C.c_int(), C.c_int()
         resid = (C.c_float * 16)()
         w = None if precond_w is None else precond_w.contiguous()
