@@ -183,6 +183,12 @@ extern "C" int gp_plan_set_comm(gp_plan* p, gp_comm* comm) {
   return GP_OK;
 }
 
+extern "C" int gp_plan_set_trace(gp_plan* p, long long* trace) {
+  GP_REQUIRE(p != nullptr, GP_E_STATE, "null plan");
+  p->tc_trace = trace;
+  return GP_OK;
+}
+
 extern "C" int64_t gp_kernel_launches(gp_plan* p) { return p ? p->launches : 0; }
 
 extern "C" int gp_plan_info(gp_plan* p, int* backend, int* nsplit, int* kpad, int* n_sm) {

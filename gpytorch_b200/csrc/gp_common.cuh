@@ -19,7 +19,7 @@ namespace gp {
 // ---- compile-time geometry ------------------------------------------------------------
 constexpr int TP = 16;         // padded column count of every [N, t] block (t <= 16)
 constexpr int TILE_I = 128;    // rows of K per CTA tile (UMMA M)
-constexpr int TILE_J = 96;     // columns of K per pipeline step (UMMA N of GEMM1, K of GEMM2)
+constexpr int TILE_J = 64;     // columns of K per pipeline step (UMMA N of GEMM1, K of GEMM2)
 constexpr int KP_MAX = 128;    // max padded augmented feature width of the tcgen05 path (3d+4 <= 128)
 constexpr int SIMT_TI = 128;   // rows per CTA in the SIMT kernel
 constexpr int SIMT_TJ = 64;    // staged columns per step in the SIMT kernel
@@ -132,6 +132,7 @@ struct gp_plan {
   gp::DevBuf pcdiag, pcperm, pcpos, pcstate, gram, cholC;
   gp_comm* comm = nullptr;
   void* pinned = nullptr;  // small pinned host scratch
+  long long* tc_trace = nullptr;  // optional device buffer [256][8] for the pipeline event trace of CTA (0,0)
 };
 
 namespace gp {

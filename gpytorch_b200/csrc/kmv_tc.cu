@@ -6,19 +6,23 @@
 //   dense K @ V inside linear_cg         lazy/lazy_evaluated_kernel_tensor.py:245-276 (chunked form)
 // The N x N matrix K never exists in HBM: per 128 x 96 tile it lives in TMEM only.
 //
-// One CTA (320 threads) owns one work unit = (128-row tile of K) x (a contiguous range of 96-column
-// tiles).  Per column tile j:
-//   GEMM1  S  = A_i . B_j^T            tcgen05.mma kind::tf32, M=128 N=96 K=KP (3xTF32 split operands packed
-//                                      by pack.cu so that S_ij = -0.5|z_i - z_j|^2 directly), S in TMEM
-//   EPI    P  = cov(S)                 two epilogue warpgroups ping-pong: tcgen05.ld -> ex2/sqrt (MUFU) ->
-//                                      P_hi/P_lo (tf32 split) -> tcgen05.st back to TMEM (P_hi in place of S)
+// One CTA (352 threads) owns one work unit = (128-row tile of K) x (a contiguous range of 64-column tiles).
+// Per column tile u (TMEM stage u % 3):
+//   GEMM1  S  = A_i . B_j^T            tcgen05.mma kind::tf32, M=128 N=64 K=KP (3xTF32 split operands packed by pack.cu so
+//                                      that S_ij = -0.5|z_i - z_j|^2 directly); runs a tile ahead of the epilogue
+//   EPI    P  = cov(S)                 two epilogue warpgroups alternate tiles: tcgen05.ld (prefetched) -> ex2/sqrt (MUFU)
+//                                      -> P_hi/P_lo (RN tf32 split) -> tcgen05.st, P_hi IN PLACE of S, P_lo next to it
 //   GEMM2  O  = P_hi [V_hi;V_lo] (N=32) + P_lo V_hi (N=16)   A operand from TMEM, B = V^T tile in smem;
 //          O is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps
-// Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact
-// UMMA K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue WG0, 4-7 epilogue
-// WG1, 8 TMA producer, 9 TMEM allocator + MMA issuer.
+// Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact UMMA
+// K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue WG0, 4-7 epilogue WG1, 8 TMA
+// producer, 9 TMEM allocator + GEMM1 issuer, 10 GEMM2 issuer (converged warps, one elect.sync per batch).
+// Measured on B200 (tools/umma_bench.cu, tools/tc_trace.py): a TS-mode MMA costs N/2 cycles (N=16: 8.7), an SS-mode one
+// ~48 at N=64; the issuing thread blocks while its MMAs execute (shallow queue) and an mbarrier wait costs ~90 cycles, so
+// GEMM1 and GEMM2 are issued from different warps and no warp waits in the middle of a tile.
 //
-// TMEM columns (512 allocated): [0,96) S0/P0hi  [96,192) P0lo  [192,288) S1/P1hi  [288,384) P1lo  [384,416) O0  [416,448) O1
+// TMEM columns (512 allocated): stage s in {0,1,2}: [s*128, +64) S -> P_hi, [s*128+64, +64) P_lo | [384,416) O of WG0 |
+//                               [416,448) O of WG1
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -26,16 +30,20 @@ namespace gp {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 320;
-constexpr int COL_S0 = 0, COL_PLO0 = 96, COL_STAGE = 192, COL_O = 384, COL_OSTAGE = 32;
-constexpr int V_TILE_BYTES = 2 * TILE_J * TP * 4;  // [96/4][32 rows: V_hi(16) | V_lo(16)][4] = 12288
-constexpr int MAX_NS = 4;
+constexpr int TC_THREADS = 352;  // 8 epilogue warps + producer + GEMM1 issuer + GEMM2 issuer
+// TMEM columns (512 allocated): three stages of [S -> P_hi in place | P_lo], then one O accumulator per warpgroup
+constexpr int COL_STAGE = 2 * TILE_J;          // stage s: S / P_hi at s*128, P_lo at s*128 + 64
+constexpr int COL_O = 3 * COL_STAGE;           // O of warpgroup g at COL_O + g*32
+static_assert(TILE_J == 64 && COL_O + 64 <= 512, "TMEM budget is laid out for TILE_J = 64");
+constexpr int V_TILE_BYTES = 2 * TILE_J * TP * 4;  // [64/4][32 rows: V_hi(16) | V_lo(16)][4] = 8192
+constexpr int MAX_NS = 6;
 
 struct TcBars {
   uint64_t a_full;
   uint64_t b_full[MAX_NS];
   uint64_t b_empty[MAX_NS];
-  uint64_t s_full[2];
+  uint64_t s_full[3];
+  uint64_t g2_done[3];   // GEMM2 finished reading stage s: GEMM1 may overwrite it
   uint64_t p_full[2];
   uint64_t o_full[2];
   uint32_t tmem_base;
@@ -46,8 +54,11 @@ template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const float* __restrict__ Vt,
               float* __restrict__ partial, int KP, int NS, int64_t ntile_j, int64_t tiles_per_split,
-              int64_t rows_pad, int same, int64_t row_begin, const int* __restrict__ done_flag) {
+              int64_t rows_pad, int same, int64_t row_begin, const int* __restrict__ done_flag, long long* __restrict__ trace) {
   if (done_flag && *done_flag) return;  // CTA-uniform, before any barrier / TMEM state exists
+  // optional event trace of CTA (0,0): trace[tile][8] = {g1_issue, g2_issue, wg_sfull_wait, wg_sfull_done, wg_c0_done, wg_ofull_done, wg_tile_end, -}
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define GP_TR(tile, ev) do { if (tr && lane == 0 && (tile) < 256) trace[(tile) * 8 + (ev)] = clock64(); } while (0)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = (int)warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -70,8 +81,11 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       mbar_init(smem_u32(&bars->b_full[s]), 1);
       mbar_init(smem_u32(&bars->b_empty[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(smem_u32(&bars->s_full[s]), 1);
+      mbar_init(smem_u32(&bars->g2_done[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->p_full[s]), 128);
       mbar_init(smem_u32(&bars->o_full[s]), 1);
     }
@@ -102,73 +116,100 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer: the whole warp runs converged, one elected lane issues ==========
+    // ===================== GEMM1 issuer (converged warp, one elected lane issues each batch) ==========
+    // GEMM1 runs ahead of the epilogue through the 3 TMEM stages; it only waits for smem tiles and for GEMM2 to have
+    // drained the stage it is about to overwrite (tile u-3).
     if (T > 0) {
-      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);   // S  = A B^T          128 x 96
-      constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);  // O += P_hi [V_hi;V_lo]^T  128 x 32
-      constexpr uint32_t IDESC2B = idesc_tf32(TILE_I, TP);      // O += P_lo V_hi^T         128 x 16
+      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);   // S = A B^T   128 x 64
       const int ksteps1 = KP / 8;
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), TILE_I * 16, 128);
       mbar_wait(smem_u32(&bars->a_full), 0);
-      int sb1 = 0, sb2 = 0;       // smem ring slots of GEMM1(u) and GEMM2(u-1)
+      int sb1 = 0;
       uint32_t par1 = 0;
-      for (int u = 0; u <= T; ++u) {
-        if (u < T) {  // GEMM1(u): S[u&1] = A . B^T
-          mbar_wait(smem_u32(&bars->b_full[sb1]), par1);
-          tc_fence_after();
-          const uint64_t b_desc0 = smem_desc(smem_u32(sStage + (size_t)sb1 * stage_bytes), TILE_J * 16, 128);
-          const uint32_t d_s = tmem + (uint32_t)((u & 1) * COL_STAGE + COL_S0);
-          for (int ks = 0; ks < ksteps1; ++ks)
-            mma_tf32_ss(d_s, a_desc0 + (uint64_t)(ks * ((2 * TILE_I * 16) >> 4)), b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)),
-                        IDESC1, ks > 0 ? 1u : 0u);
-          tc_commit(smem_u32(&bars->s_full[u & 1]));
-          if (++sb1 == NS) { sb1 = 0; par1 ^= 1; }
-        }
-        if (u >= 1) {  // GEMM2(u-1): O[v&1] = P . V   (fresh accumulator every tile, see epilogue)
-          const int v = u - 1;
-          mbar_wait(smem_u32(&bars->p_full[v & 1]), (v >> 1) & 1);
-          tc_fence_after();
-          const uint64_t v_desc0 = smem_desc(smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes), 2 * TP * 16, 128);
-          const uint32_t p_hi = tmem + (uint32_t)((v & 1) * COL_STAGE + COL_S0);
-          const uint32_t p_lo = tmem + (uint32_t)((v & 1) * COL_STAGE + COL_PLO0);
-          const uint32_t d_o = tmem + (uint32_t)(COL_O + (v & 1) * COL_OSTAGE);
+      for (int u = 0; u < T; ++u) {
+        const int slot = u % 3, use = u / 3;
+        mbar_wait(smem_u32(&bars->b_full[sb1]), par1);
+        if (use > 0) mbar_wait(smem_u32(&bars->g2_done[slot]), (uint32_t)((use - 1) & 1));
+        tc_fence_after();
+        GP_TR(u, 0);
+        const uint64_t b_desc0 = smem_desc(smem_u32(sStage + (size_t)sb1 * stage_bytes), TILE_J * 16, 128);
+        const uint32_t d_s = tmem + (uint32_t)(slot * COL_STAGE);
+        const uint32_t sfull = smem_u32(&bars->s_full[slot]);
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < TILE_J / 8; ++ks)
-            mma_tf32_ts(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < TILE_J / 8; ++ks)
-            mma_tf32_ts(d_o, p_lo + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2B, 1u);
-          tc_commit(smem_u32(&bars->b_empty[sb2]));     // smem slot (B + V) and P[v&1] are free again
-          tc_commit(smem_u32(&bars->o_full[v & 1]));    // O[v&1] holds tile v's product
-          if (++sb2 == NS) sb2 = 0;
+          for (int ks = 0; ks < KP_MAX / 8; ++ks)  // fully unrolled + predicated: keeps every operand in uniform registers
+            if (ks < ksteps1)
+              mma_tf32_ss_1t(d_s, a_desc0 + (uint64_t)(ks * ((2 * TILE_I * 16) >> 4)), b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)),
+                             IDESC1, ks > 0 ? 1u : 0u);
+          tc_commit_1t(sfull);
         }
+        __syncwarp();
+        if (++sb1 == NS) { sb1 = 0; par1 ^= 1; }
       }
     }
-  } else {
+  } else if (warp == 10) {
+    // ===================== GEMM2 issuer ==========
+    // O[u&1] = P_hi [V_hi;V_lo]^T (N=32) + P_lo V_hi^T (N=16); a fresh accumulator per tile (folded by the epilogue).
+    constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);
+    constexpr uint32_t IDESC2B = idesc_tf32(TILE_I, TP);
+    int sb2 = 0;
+    for (int u = 0; u < T; ++u) {
+      const int stage = u % 3;
+      mbar_wait(smem_u32(&bars->p_full[u & 1]), (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      GP_TR(u, 1);
+      const uint64_t v_desc0 = smem_desc(smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes), 2 * TP * 16, 128);
+      const uint32_t p_hi = tmem + (uint32_t)(stage * COL_STAGE);
+      const uint32_t p_lo = p_hi + TILE_J;
+      const uint32_t d_o = tmem + (uint32_t)(COL_O + (u & 1) * 2 * TP);
+      const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full[u & 1]),
+                     g2d = smem_u32(&bars->g2_done[stage]);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TILE_J / 8; ++ks)
+          mma_tf32_ts_1t(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < TILE_J / 8; ++ks)
+          mma_tf32_ts_1t(d_o, p_lo + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2B, 1u);
+        tc_commit_1t(bempty);   // smem slot (B + V) is free again
+        tc_commit_1t(ofull);    // O[u&1] holds tile u's product
+        tc_commit_1t(g2d);      // TMEM stage may be refilled by GEMM1(u+3)
+      }
+      __syncwarp();
+      if (++sb2 == NS) sb2 = 0;
+    }
+  } else if (warp < 8) {
     // ===================== epilogue warpgroups =====================
     const int wg = warp >> 2;          // 0 or 1: handles tiles u = wg, wg+2, ...
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int64_t gi = row_begin + it * TILE_I + q * 32 + lane;  // global row of this thread
-    const uint32_t t_s = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_S0);
-    const uint32_t t_lo = tmem + lane_off + (uint32_t)(wg * COL_STAGE + COL_PLO0);
-    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * COL_OSTAGE);
-    // O is flushed into fp32 registers after EVERY tile: the tensor core's accumulator truncates on each add,
-    // so long TMEM accumulation chains drift (1e-4 at N = 50k); 36 adds per tile keep it at ~1e-6.
+    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * 2 * TP);
+    // O is folded into fp32 registers after EVERY tile: the tensor core's accumulator truncates on each add, so long
+    // TMEM accumulation chains drift (1e-4 at N = 50k); 16 adds per tile keep the product at fp32 level.
     float acc[TP];
 #pragma unroll
     for (int c = 0; c < TP; ++c) acc[c] = 0.f;
-    int npend = 0;  // tiles whose O has not been folded into acc yet (0 or 1)
+    int npend = 0;  // 1 when the previous tile's O has not been folded into acc yet
     for (int u = wg; u < T; u += 2) {
-      mbar_wait(smem_u32(&bars->s_full[wg]), (u >> 1) & 1);
+      const int stage = u % 3;
+      if (q == 0) GP_TR(u, 2);
+      mbar_wait(smem_u32(&bars->s_full[stage]), (uint32_t)((u / 3) & 1));
       tc_fence_after();
+      if (q == 0) GP_TR(u, 3);
+      const uint32_t t_s = tmem + lane_off + (uint32_t)(stage * COL_STAGE);   // S, overwritten in place by P_hi
+      const uint32_t t_lo = t_s + TILE_J;
       const int64_t jbase = (jt0 + u) * TILE_J;
       const bool diag_tile = same && (row_begin + it * TILE_I < jbase + TILE_J) && (jbase < row_begin + (it + 1) * TILE_I);
-#pragma unroll 1
+      uint32_t rn[32];
+      GP_TMEM_LD32(t_s, rn);  // prefetch chunk 0
+#pragma unroll
       for (int ch = 0; ch < TILE_J / 32; ++ch) {
         uint32_t r[32], lo[32];
-        GP_TMEM_LD32(t_s + ch * 32, r);
         tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = rn[c];
+        if (ch + 1 < TILE_J / 32) GP_TMEM_LD32(t_s + (ch + 1) * 32, rn);  // prefetch the next chunk behind the math
         if (diag_tile) {
           const int cd = (int)(gi - (jbase + ch * 32));
 #pragma unroll
@@ -182,26 +223,30 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
           lo[c] = __float_as_uint(p - __uint_as_float(hi));
           r[c] = hi;
         }
+        if (ch == 0 && q == 0) GP_TR(u, 4);
         GP_TMEM_ST32(t_s + ch * 32, r);
         GP_TMEM_ST32(t_lo + ch * 32, lo);
       }
-      if (npend) {  // fold the previous tile's O (GEMM2(u-2) finished long ago) before releasing P(u)
-        mbar_wait(smem_u32(&bars->o_full[wg]), ((u - 2) >> 1) & 1);
+      if (npend) {
+        // GEMM2(u-2) was issued a whole tile ago: its O is complete; fold it before GEMM2(u) overwrites O[wg]
+        mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)(((u - 2) >> 1) & 1));
         tc_fence_after();
         uint32_t o[32];
         GP_TMEM_LD32(t_o, o);
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
+        if (q == 0) GP_TR(u, 5);
       }
       npend = 1;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[wg]));  // GEMM2(u) may now overwrite O[wg] and read P[wg]
+      mbar_arrive(smem_u32(&bars->p_full[wg]));  // GEMM2(u) may now read P (this stage) and overwrite O[wg]
+      if (q == 0) GP_TR(u, 6);
     }
     if (npend) {
       const int ulast = wg + 2 * ((T - 1 - wg) / 2);
-      mbar_wait(smem_u32(&bars->o_full[wg]), (ulast >> 1) & 1);
+      mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)((ulast >> 1) & 1));
       tc_fence_after();
       uint32_t o[32];
       GP_TMEM_LD32(t_o, o);
@@ -237,7 +282,7 @@ template <int KIND>
 static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   int ns = 0;
   int smem_bytes = tc_smem_bytes(p->KP, &ns);
-  GP_REQUIRE(ns >= 2, GP_E_SHAPE, "tcgen05 path: smem ring too small for KP=%d", p->KP);
+  GP_REQUIRE(ns >= 3, GP_E_SHAPE, "tcgen05 path: smem ring too small for KP=%d", p->KP);
   static bool attr_done[4] = {false, false, false, false};
   if (!attr_done[KIND]) {
     GP_CUDA(cudaFuncSetAttribute(kmv_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -247,7 +292,7 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   dim3 grid((unsigned)p->ntile_i, (unsigned)p->nsplit);
   kmv_tc_kernel<KIND><<<grid, TC_THREADS, smem_bytes, p->stream>>>(
       p->XA.as<float>(), p->XB.as<float>(), p->Vtiles.as<float>(), p->partial.as<float>(), p->KP, ns, p->ntile_j,
-      p->tiles_per_split, rows_pad, p->same ? 1 : 0, p->row_begin, done_flag);
+      p->tiles_per_split, rows_pad, p->same ? 1 : 0, p->row_begin, done_flag, p->tc_trace);
   p->launches++;
   GP_CUDA(cudaGetLastError());
   return GP_OK;

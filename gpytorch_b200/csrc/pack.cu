@@ -10,9 +10,9 @@
 //   Z1   [n1_local][DP]      only when X2 != X1 (otherwise Z1 aliases Z2 + row_begin*DP)
 //   XA   [ntile_i][KP/4][128][4]   UMMA K-major no-swizzle tiles of the A operand
 //                                  [z_hi | z_lo | z_hi | n_hi n_lo 1 1 | 0..]   (3xTF32 split)
-//   XB   [ntile_j][KP/4][ 96][4]   B operand  [z_hi | z_hi | z_lo | 1 1 n_hi n_lo | 0..]
+//   XB   [ntile_j][KP/4][ 64][4]   B operand  [z_hi | z_hi | z_lo | 1 1 n_hi n_lo | 0..]
 //   so that  sum_k A_ik B_jk = z_i.z_j (to ~2^-22) + n_i + n_j,  n = -0.5 |z|^2  = a_ij.
-//   Vt   [ntile_j][96/4][32][4]    V^T tiles, rows 0-15 = tf32 hi, rows 16-31 = tf32 lo (B operand of GEMM2)
+//   Vt   [ntile_j][64/4][32][4]    V^T tiles, rows 0-15 = tf32 hi, rows 16-31 = tf32 lo (B operand of GEMM2)
 #include "gp_common.cuh"
 
 namespace gp {

@@ -170,6 +170,9 @@ int64_t gp_kernel_launches(gp_plan* plan);               /* kernels launched by 
 int gp_plan_info(gp_plan* plan, int* backend, int* nsplit, int* kpad, int* n_sm);
 /* Times `reps` back-to-back launches of the fused K.V kernel ALONE (after `warmup` untimed ones) with CUDA
  * events on the plan's stream; V [n2, t].  *ms_per_launch is the average device time of one launch. */
+/* Debug: device buffer of 256*8 int64 receiving clock64() stamps of the tcgen05 pipeline events of CTA (0,0)
+ * (NULL disables).  Used by tools/tc_trace.py to study pipeline bubbles. */
+int gp_plan_set_trace(gp_plan* plan, long long* trace);
 int gp_time_kmv_kernel(gp_plan* plan, const float* V, int64_t ldv, int t, int warmup, int reps, float* ms_per_launch);
 
 #ifdef __cplusplus
