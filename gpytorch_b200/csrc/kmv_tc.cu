@@ -7,22 +7,22 @@
 // The N x N matrix K never exists in HBM: per 128 x 96 tile it lives in TMEM only.
 //
 // One CTA (352 threads) owns one work unit = (128-row tile of K) x (a contiguous range of 64-column tiles).
-// Per column tile u (TMEM stage u % 3):
+// Per column tile u (TMEM stage u % 4):
 //   GEMM1  S  = A_i . B_j^T            tcgen05.mma kind::tf32, M=128 N=64 K=KP (3xTF32 split operands packed by pack.cu so
 //                                      that S_ij = -0.5|z_i - z_j|^2 directly); runs a tile ahead of the epilogue
 //   EPI    P  = cov(S)                 two epilogue warpgroups alternate tiles: tcgen05.ld (prefetched) -> ex2/sqrt (MUFU)
 //                                      -> P_hi/P_lo (RN tf32 split) -> tcgen05.st, P_hi IN PLACE of S, P_lo next to it
-//   GEMM2  O  = P_hi [V_hi;V_lo] (N=32) + P_lo V_hi (N=16)   A operand from TMEM, B = V^T tile in smem;
+//   GEMM2  O  = P_hi [V_hi;V_lo] (tf32, N=32) + P_lo V (bf16 x bf16, N=16)   A operand from TMEM, B = V^T tiles in smem;
 //          O is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps
 // Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact UMMA
 // K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue WG0, 4-7 epilogue WG1, 8 TMA
-// producer, 9 TMEM allocator + GEMM1 issuer, 10 GEMM2 issuer (converged warps, one elect.sync per batch).
+// producer, 9 TMEM allocator + GEMM1 issuer, 10/11 GEMM2 issuers of WG0/WG1 (converged warps, one elect.sync per batch).
 // Measured on B200 (tools/umma_bench.cu, tools/tc_trace.py): a TS-mode MMA costs N/2 cycles (N=16: 8.7), an SS-mode one
 // ~48 at N=64; the issuing thread blocks while its MMAs execute (shallow queue) and an mbarrier wait costs ~90 cycles, so
 // GEMM1 and GEMM2 are issued from different warps and no warp waits in the middle of a tile.
 //
-// TMEM columns (512 allocated): stage s in {0,1,2}: [s*128, +64) S -> P_hi, [s*128+64, +64) P_lo | [384,416) O of WG0 |
-//                               [416,448) O of WG1
+// TMEM columns (512 allocated): stage s in {0..3}: [s*96, +64) S -> P_hi (tf32), [s*96+64, +32) P_lo (bf16 pairs) |
+//                               [384,416) O of WG0 | [416,448) O of WG1
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,20 +30,24 @@ namespace gp {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 352;  // 8 epilogue warps + producer + GEMM1 issuer + GEMM2 issuer
-// TMEM columns (512 allocated): three stages of [S -> P_hi in place | P_lo], then one O accumulator per warpgroup
-constexpr int COL_STAGE = 2 * TILE_J;          // stage s: S / P_hi at s*128, P_lo at s*128 + 64
-constexpr int COL_O = 3 * COL_STAGE;           // O of warpgroup g at COL_O + g*32
+constexpr int TC_THREADS = 384;  // 8 epilogue warps + producer + GEMM1 issuer + two GEMM2 issuers
+// TMEM columns (512 allocated): NSTG stages of [S -> P_hi (tf32) in place | P_lo (bf16, 2 per column)], then one O
+// accumulator per warpgroup
+constexpr int NSTG = 4;
+constexpr int COL_STAGE = TILE_J + TILE_J / 2; // stage s: S / P_hi at s*96 (64 columns), P_lo at s*96 + 64 (32 columns)
+constexpr int COL_O = NSTG * COL_STAGE;        // O of warpgroup g at COL_O + g*32
 static_assert(TILE_J == 64 && COL_O + 64 <= 512, "TMEM budget is laid out for TILE_J = 64");
-constexpr int V_TILE_BYTES = 2 * TILE_J * TP * 4;  // [64/4][32 rows: V_hi(16) | V_lo(16)][4] = 8192
+constexpr int V_TF32_BYTES = 2 * TILE_J * TP * 4;  // [64/4][32 rows: V_hi(16) | V_lo(16)][4 tf32] = 8192
+constexpr int V_BF16_BYTES = TILE_J * TP * 2;      // [64/8][16 rows][8 bf16]                       = 2048
+constexpr int V_TILE_BYTES = V_TF32_BYTES + V_BF16_BYTES;
 constexpr int MAX_NS = 6;
 
 struct TcBars {
   uint64_t a_full;
   uint64_t b_full[MAX_NS];
   uint64_t b_empty[MAX_NS];
-  uint64_t s_full[3];
-  uint64_t g2_done[3];   // GEMM2 finished reading stage s: GEMM1 may overwrite it
+  uint64_t s_full[NSTG];
+  uint64_t g2_done[NSTG];   // GEMM2 finished reading stage s: GEMM1 may overwrite it
   uint64_t p_full[2];
   uint64_t o_full[2];
   uint32_t tmem_base;
@@ -81,7 +85,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       mbar_init(smem_u32(&bars->b_full[s]), 1);
       mbar_init(smem_u32(&bars->b_empty[s]), 1);
     }
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(smem_u32(&bars->s_full[s]), 1);
       mbar_init(smem_u32(&bars->g2_done[s]), 1);
     }
@@ -111,7 +115,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         const int64_t jt = jt0 + u;
         mbar_arrive_expect_tx(full, stage_bytes);
         bulk_g2s(smem_u32(st), XB + jt * (int64_t)TILE_J * KP, b_bytes, full);
-        bulk_g2s(smem_u32(st + b_bytes), Vt + jt * (int64_t)(2 * TILE_J * TP), V_TILE_BYTES, full);
+        bulk_g2s(smem_u32(st + b_bytes), reinterpret_cast<const uint8_t*>(Vt) + jt * (int64_t)V_TILE_BYTES, V_TILE_BYTES, full);
         if (++sb == NS) { sb = 0; par ^= 1; }
       }
     }
@@ -127,7 +131,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       int sb1 = 0;
       uint32_t par1 = 0;
       for (int u = 0; u < T; ++u) {
-        const int slot = u % 3, use = u / 3;
+        const int slot = u % NSTG, use = u / NSTG;
         mbar_wait(smem_u32(&bars->b_full[sb1]), par1);
         if (use > 0) mbar_wait(smem_u32(&bars->g2_done[slot]), (uint32_t)((use - 1) & 1));
         tc_fence_after();
@@ -147,36 +151,40 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         if (++sb1 == NS) { sb1 = 0; par1 ^= 1; }
       }
     }
-  } else if (warp == 10) {
-    // ===================== GEMM2 issuer ==========
-    // O[u&1] = P_hi [V_hi;V_lo]^T (N=32) + P_lo V_hi^T (N=16); a fresh accumulator per tile (folded by the epilogue).
+  } else if (warp >= 10) {
+    // ===================== GEMM2 issuers: warp 10 serves warpgroup 0's tiles (even u), warp 11 warpgroup 1's ==========
+    // O[g] = P_hi [V_hi;V_lo]^T (tf32, N=32) + P_lo V^T (bf16 x bf16, N=16); a fresh accumulator per tile.
+    const int g = warp - 10;
     constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);
-    constexpr uint32_t IDESC2B = idesc_tf32(TILE_I, TP);
-    int sb2 = 0;
-    for (int u = 0; u < T; ++u) {
-      const int stage = u % 3;
-      mbar_wait(smem_u32(&bars->p_full[u & 1]), (uint32_t)((u >> 1) & 1));
+    constexpr uint32_t IDESC2B = idesc_bf16(TILE_I, TP);
+    const uint32_t d_o = tmem + (uint32_t)(COL_O + g * 2 * TP);
+    int sb2 = g % NS;
+    for (int u = g; u < T; u += 2) {
+      const int stage = u % NSTG;
+      mbar_wait(smem_u32(&bars->p_full[g]), (uint32_t)((u >> 1) & 1));
       tc_fence_after();
       GP_TR(u, 1);
-      const uint64_t v_desc0 = smem_desc(smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes), 2 * TP * 16, 128);
+      const uint32_t v_addr = smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes);
+      const uint64_t v_desc0 = smem_desc(v_addr, 2 * TP * 16, 128);                 // tf32 tile, 32 rows
+      const uint64_t w_desc0 = smem_desc(v_addr + V_TF32_BYTES, TP * 16, 128);      // bf16 tile, 16 rows
       const uint32_t p_hi = tmem + (uint32_t)(stage * COL_STAGE);
       const uint32_t p_lo = p_hi + TILE_J;
-      const uint32_t d_o = tmem + (uint32_t)(COL_O + (u & 1) * 2 * TP);
-      const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full[u & 1]),
+      const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full[g]),
                      g2d = smem_u32(&bars->g2_done[stage]);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < TILE_J / 8; ++ks)
           mma_tf32_ts_1t(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < TILE_J / 8; ++ks)
-          mma_tf32_ts_1t(d_o, p_lo + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2B, 1u);
+        for (int ks = 0; ks < TILE_J / 16; ++ks)
+          mma_bf16_ts_1t(d_o, p_lo + ks * 8, w_desc0 + (uint64_t)(ks * ((2 * TP * 16) >> 4)), IDESC2B, 1u);
         tc_commit_1t(bempty);   // smem slot (B + V) is free again
-        tc_commit_1t(ofull);    // O[u&1] holds tile u's product
-        tc_commit_1t(g2d);      // TMEM stage may be refilled by GEMM1(u+3)
+        tc_commit_1t(ofull);    // O[g] holds tile u's product
+        tc_commit_1t(g2d);      // TMEM stage may be refilled by GEMM1(u + NSTG)
       }
       __syncwarp();
-      if (++sb2 == NS) sb2 = 0;
+      sb2 += 2;
+      while (sb2 >= NS) sb2 -= NS;
     }
   } else if (warp < 8) {
     // ===================== epilogue warpgroups =====================
@@ -192,9 +200,9 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
     for (int c = 0; c < TP; ++c) acc[c] = 0.f;
     int npend = 0;  // 1 when the previous tile's O has not been folded into acc yet
     for (int u = wg; u < T; u += 2) {
-      const int stage = u % 3;
+      const int stage = u % NSTG;
       if (q == 0) GP_TR(u, 2);
-      mbar_wait(smem_u32(&bars->s_full[stage]), (uint32_t)((u / 3) & 1));
+      mbar_wait(smem_u32(&bars->s_full[stage]), (uint32_t)((u / NSTG) & 1));
       tc_fence_after();
       if (q == 0) GP_TR(u, 3);
       const uint32_t t_s = tmem + lane_off + (uint32_t)(stage * COL_STAGE);   // S, overwritten in place by P_hi
@@ -205,7 +213,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       GP_TMEM_LD32(t_s, rn);  // prefetch chunk 0
 #pragma unroll
       for (int ch = 0; ch < TILE_J / 32; ++ch) {
-        uint32_t r[32], lo[32];
+        uint32_t r[32], lo[16];
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 32; ++c) r[c] = rn[c];
@@ -217,15 +225,19 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
             if (c == cd) r[c] = 0u;  // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float p = cov_from_arg<KIND>(__uint_as_float(r[c]));
-          uint32_t hi = (__float_as_uint(p) + 0x1000u) & 0xFFFFE000u;  // RN to tf32
-          lo[c] = __float_as_uint(p - __uint_as_float(hi));
-          r[c] = hi;
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = cov_from_arg<KIND>(__uint_as_float(r[c]));
+          float p1 = cov_from_arg<KIND>(__uint_as_float(r[c + 1]));
+          uint32_t h0 = (__float_as_uint(p0) + 0x1000u) & 0xFFFFE000u;  // RN to tf32
+          uint32_t h1 = (__float_as_uint(p1) + 0x1000u) & 0xFFFFE000u;
+          // the residual (<= 2^-12 p) only needs ~8 more bits: bf16, two per TMEM column, keeps P to ~2^-21 relative
+          lo[c >> 1] = pack_bf16x2(p0 - __uint_as_float(h0), p1 - __uint_as_float(h1));
+          r[c] = h0;
+          r[c + 1] = h1;
         }
         if (ch == 0 && q == 0) GP_TR(u, 4);
         GP_TMEM_ST32(t_s + ch * 32, r);
-        GP_TMEM_ST32(t_lo + ch * 32, lo);
+        GP_TMEM_ST16(t_lo + ch * 16, lo);
       }
       if (npend) {
         // GEMM2(u-2) was issued a whole tile ago: its O is complete; fold it before GEMM2(u) overwrites O[wg]

@@ -12,7 +12,7 @@
 //                                  [z_hi | z_lo | z_hi | n_hi n_lo 1 1 | 0..]   (3xTF32 split)
 //   XB   [ntile_j][KP/4][ 64][4]   B operand  [z_hi | z_hi | z_lo | 1 1 n_hi n_lo | 0..]
 //   so that  sum_k A_ik B_jk = z_i.z_j (to ~2^-22) + n_i + n_j,  n = -0.5 |z|^2  = a_ij.
-//   Vt   [ntile_j][64/4][32][4]    V^T tiles, rows 0-15 = tf32 hi, rows 16-31 = tf32 lo (B operand of GEMM2)
+//   Vt   per 64-row tile: [64/4][32][4] tf32 (rows 0-15 hi, 16-31 lo) + [64/8][16][8] bf16  (B operands of GEMM2)
 #include "gp_common.cuh"
 
 namespace gp {
@@ -93,7 +93,10 @@ __global__ void to_v16_kernel(const float* __restrict__ V, int64_t ldv, int t, i
   V16[idx] = (c < t) ? V[r * ldv + c] : 0.f;
 }
 
-// thread per (4-row chunk, column): V16 [n2][16] -> Vt tiles (hi, lo)
+// thread per (4-row chunk, column): V16 [n2][16] -> Vt tiles.  Per 64-row tile (10240 B):
+//   [0, 8192)      tf32 tile  [64/4][32 rows][4]: rows 0-15 = hi, rows 16-31 = lo of the 16 columns
+//   [8192, 10240)  bf16 tile  [64/8][16 rows][8]: bf16(v), the B operand of the P_lo pass
+constexpr int V_TILE_FLOATS = (2 * TILE_J * TP * 4 + TILE_J * TP * 2) / 4;  // 2560
 __global__ void pack_v_tiles_kernel(const float* __restrict__ V16, int64_t n2, int64_t ntile_j, float* __restrict__ Vt) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t nchunk = ntile_j * (TILE_J / 4);
@@ -103,17 +106,24 @@ __global__ void pack_v_tiles_kernel(const float* __restrict__ V16, int64_t n2, i
   int64_t tile = chunk / (TILE_J / 4);
   int kc = (int)(chunk % (TILE_J / 4));
   int64_t j0 = tile * TILE_J + kc * 4;
-  float hi[4], lo[4];
+  float hi[4], lo[4], v[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     int64_t j = j0 + q;
-    float v = (j < n2) ? V16[j * TP + c] : 0.f;
-    hi[q] = tf32_hi(v);
-    lo[q] = tf32_hi(v - hi[q]);
+    v[q] = (j < n2) ? V16[j * TP + c] : 0.f;
+    hi[q] = tf32_hi(v[q]);
+    lo[q] = tf32_hi(v[q] - hi[q]);
   }
-  float4* base = reinterpret_cast<float4*>(Vt + tile * (int64_t)(2 * TILE_J * TP));
+  float* tbase = Vt + tile * (int64_t)V_TILE_FLOATS;
+  float4* base = reinterpret_cast<float4*>(tbase);
   base[kc * (2 * TP) + c] = make_float4(hi[0], hi[1], hi[2], hi[3]);        // B rows 0..15  = V_hi columns
   base[kc * (2 * TP) + TP + c] = make_float4(lo[0], lo[1], lo[2], lo[3]);   // B rows 16..31 = V_lo columns
+  // bf16 tile: element (row c, k = kc*4+q) at [(k/8)][c][k%8]
+  uint32_t w0, w1;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(v[1]), "f"(v[0]));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(v[3]), "f"(v[2]));
+  uint2* wb = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(tbase) + 2 * TILE_J * TP * 4);
+  wb[((kc >> 1) * TP + c) * 2 + (kc & 1)] = make_uint2(w0, w1);
 }
 
 static int round_dp(int d) {
@@ -198,7 +208,7 @@ int pack_inputs(gp_plan* p) {
     pack_tc_kernel<true><<<(unsigned)cdiv(padA, 128), 128, 0, st>>>(ZA, rowA0, p->row_count, padA, d, DP, KP, TILE_I, p->XA.as<float>());
     pack_tc_kernel<false><<<(unsigned)cdiv(padB, 128), 128, 0, st>>>(p->Z2.as<float>(), 0, p->n2, padB, d, DP, KP, TILE_J, p->XB.as<float>());
     p->launches += 2;
-    GP_CHECK(p->Vtiles.ensure(sizeof(float) * p->ntile_j * 2 * TILE_J * TP));
+    GP_CHECK(p->Vtiles.ensure(sizeof(float) * p->ntile_j * (2 * TILE_J * TP + TILE_J * TP / 2)));
   }
   int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
   p->nparts = p->nsplit * (p->backend == GP_BACKEND_TCGEN05 ? 2 : 1);  // tcgen05: one slot per epilogue warpgroup
