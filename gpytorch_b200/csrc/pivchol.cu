@@ -23,7 +23,7 @@ struct PcState {
   unsigned int counter;  // last-block-done ticket
 };
 
-constexpr int PC_THREADS = 256;
+constexpr int PC_THREADS = 128;
 
 // One launch per step m, fused: row update with the pivot chosen by the previous launch,
 // then -- in the same pass -- the per-CTA (max, earliest permutation position, sum |diag|) over the remaining
@@ -66,7 +66,19 @@ pc_step_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict_
         s = fmaf(df, df, s);
       }
       float v = os * cov_from_arg<KIND>(-0.5f * s);
-      for (int q = 0; q < m; ++q) v = fmaf(-lp[q], Lt[(int64_t)q * n + j], v);
+      {
+        // independent partial sums keep 8 L2 loads in flight per thread (the step is latency bound, not bandwidth bound)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int q = 0;
+        for (; q + 4 <= m; q += 4) {
+          s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
+          s1 = fmaf(lp[q + 1], Lt[(int64_t)(q + 1) * n + j], s1);
+          s2 = fmaf(lp[q + 2], Lt[(int64_t)(q + 2) * n + j], s2);
+          s3 = fmaf(lp[q + 3], Lt[(int64_t)(q + 3) * n + j], s3);
+        }
+        for (; q < m; ++q) s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
+        v -= (s0 + s1) + (s2 + s3);
+      }
       v /= dpiv;
       Lm[j] = v;
       float dn = diag[j] - v * v;
