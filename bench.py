@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if not os.environ.get("GP_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
 
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on

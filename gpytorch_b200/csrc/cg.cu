@@ -113,75 +113,110 @@ __global__ void cg_init_kernel(const float* __restrict__ RHS, int64_t ldr, int t
   block_reduce_cols(acc, red, part + (size_t)blockIdx.x * TP);
 }
 
-// partial QtR[blk][kk*16 + c] = sum_rows W[r][kk] R[r][c]
-__global__ void cg_qtr_kernel(const float* __restrict__ W, int k, const float* __restrict__ R, int64_t n,
-                              float* __restrict__ part, int L, int off, const int* done) {
+// partial QtR[blk][kk*16 + c] = sum_rows W[r][kk] R[r][c]     (skinny GEMM, [k x rows] . [rows x 16])
+// Register tile of 4 (kk) x 4 (c) per thread; thread = (half, kg, cg): 2 row halves x 32 kk-groups x 4 column groups.
+__global__ void __launch_bounds__(CG_THREADS)
+cg_qtr_kernel(const float* __restrict__ W, int k, const float* __restrict__ R, int64_t n,
+              float* __restrict__ part, int L, int off, const int* done) {
   if (done && *done) return;
   extern __shared__ __align__(16) float sh[];
-  float* Ws = sh;               // [32][k]
-  float* Rs = sh + 32 * k;      // [32][16]
-  const int tid = threadIdx.x, c = tid & 15, kg = tid >> 4;
-  float acc[KMAX / 16];
+  const int kp = (k + 3) & ~3;   // row pitch of the staged W chunk (multiple of 4 for float4 reads)
+  float* Ws = sh;                // [32][kp]
+  float* Rs = sh + 32 * kp;      // [32][16]
+  const int tid = threadIdx.x, cg = tid & 3, kg = (tid >> 2) & 31, half = tid >> 7;
+  const bool act = kg * 4 < k;
+  float acc[4][4];
 #pragma unroll
-  for (int m = 0; m < KMAX / 16; ++m) acc[m] = 0.f;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < n; r0 += (int64_t)gridDim.x * 32) {
     const int nr = (int)min((int64_t)32, n - r0);
     __syncthreads();
-    for (int e = tid; e < 32 * k; e += CG_THREADS) Ws[e] = (e / k < nr) ? W[r0 * k + e] : 0.f;
+    for (int e = tid; e < 32 * kp; e += CG_THREADS) {
+      int rr = e / kp, kk = e - rr * kp;
+      Ws[e] = (rr < nr && kk < k) ? W[(r0 + rr) * k + kk] : 0.f;
+    }
     for (int e = tid; e < 32 * TP; e += CG_THREADS) Rs[e] = (e / TP < nr) ? R[r0 * TP + e] : 0.f;
     __syncthreads();
-    for (int rr = 0; rr < 32; ++rr) {
-      const float rv = Rs[rr * TP + c];
+    if (act) {
+#pragma unroll 4
+      for (int rr = half; rr < 32; rr += 2) {
+        const float4 wv = *reinterpret_cast<const float4*>(&Ws[rr * kp + kg * 4]);
+        const float4 rv = *reinterpret_cast<const float4*>(&Rs[rr * TP + cg * 4]);
+        const float w4[4] = {wv.x, wv.y, wv.z, wv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-      for (int m = 0; m < KMAX / 16; ++m) {
-        int kk = kg + 16 * m;
-        if (kk < k) acc[m] = fmaf(Ws[rr * k + kk], rv, acc[m]);
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(w4[a], r4[b], acc[a][b]);
       }
     }
   }
-  float* o = part + (size_t)blockIdx.x * L + off;
+  // combine the two row halves through shared memory (fixed order), then write the CTA partial
+  __syncthreads();
+  float* red = sh;  // reuse: [128][16]
+  if (half == 1 && act) {
 #pragma unroll
-  for (int m = 0; m < KMAX / 16; ++m) {
-    int kk = kg + 16 * m;
-    if (kk < k) o[kk * TP + c] = acc[m];
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) red[((kg * 4 + a) * 4 + cg) * 4 + b] = acc[a][b];
+  }
+  __syncthreads();
+  if (half == 0 && act) {
+    float* o = part + (size_t)blockIdx.x * L + off;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int kk = kg * 4 + a;
+      if (kk < k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o[kk * TP + cg * 4 + b] = acc[a][b] + red[((kg * 4 + a) * 4 + cg) * 4 + b];
+      }
+    }
   }
 }
 
 // Z = (R - W w) / noise ; partial zr = sum Z.R      (w = all-reduced QtR, fp64 [k][16])
-__global__ void cg_precond_kernel(const float* __restrict__ W, int k, const double* __restrict__ w, float inv_noise,
-                                  const float* __restrict__ R, float* __restrict__ Z, int64_t n, float* __restrict__ part,
-                                  const int* done) {
+// thread = (row lane, 4 columns); W rows are streamed from global/L2 as float4, w sits in shared memory.
+__global__ void __launch_bounds__(CG_THREADS)
+cg_precond_kernel(const float* __restrict__ W, int k, const double* __restrict__ w, float inv_noise,
+                  const float* __restrict__ R, float* __restrict__ Z, int64_t n, float* __restrict__ part,
+                  const int* done) {
   if (done && *done) return;
   extern __shared__ __align__(16) float sh[];
-  float* ws = sh;                 // [k][16]
-  float* Ws = sh + k * TP;        // [16][k]
-  float* red = Ws + 16 * k;       // [16][16]
-  const int tid = threadIdx.x, c = tid & 15, rs = tid >> 4;
+  float* ws = sh;                                 // [k][16]
+  float* red = sh + ((k * TP + 3) & ~3);          // [CG_ROWS][16]
+  const int tid = threadIdx.x, cg = tid & 3, rl = tid >> 2;
   for (int e = tid; e < k * TP; e += CG_THREADS) ws[e] = (float)w[e];
-  float zr = 0.f;
-  for (int64_t r0 = (int64_t)blockIdx.x * 16; r0 < n; r0 += (int64_t)gridDim.x * 16) {
-    const int nr = (int)min((int64_t)16, n - r0);
-    __syncthreads();
-    for (int e = tid; e < 16 * k; e += CG_THREADS) Ws[e] = (e / k < nr) ? W[r0 * k + e] : 0.f;
-    __syncthreads();
-    if (rs < nr) {
-      const int64_t r = r0 + rs;
-      float rv = R[r * TP + c];
-      float s = 0.f;
-      for (int kk = 0; kk < k; ++kk) s = fmaf(Ws[rs * k + kk], ws[kk * TP + c], s);
-      float z = (rv - s) * inv_noise;
-      Z[r * TP + c] = z;
-      zr = fmaf(z, rv, zr);
+  __syncthreads();
+  const bool vec = (k & 3) == 0;
+  float4 acc = make_float4(0, 0, 0, 0);
+  for (int64_t r = (int64_t)blockIdx.x * CG_ROWS + rl; r < n; r += (int64_t)gridDim.x * CG_ROWS) {
+    const float* wr = W + r * k;
+    float4 s = make_float4(0, 0, 0, 0);
+    int kk = 0;
+    if (vec) {
+      for (; kk < k; kk += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + kk);
+        const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 c4 = *reinterpret_cast<const float4*>(&ws[(kk + a) * TP + cg * 4]);
+          s.x = fmaf(w4[a], c4.x, s.x); s.y = fmaf(w4[a], c4.y, s.y); s.z = fmaf(w4[a], c4.z, s.z); s.w = fmaf(w4[a], c4.w, s.w);
+        }
+      }
+    } else {
+      for (; kk < k; ++kk) {
+        const float wv = wr[kk];
+        const float4 c4 = *reinterpret_cast<const float4*>(&ws[kk * TP + cg * 4]);
+        s.x = fmaf(wv, c4.x, s.x); s.y = fmaf(wv, c4.y, s.y); s.z = fmaf(wv, c4.z, s.z); s.w = fmaf(wv, c4.w, s.w);
+      }
     }
+    const float4 rv = reinterpret_cast<const float4*>(R)[r * 4 + cg];
+    float4 z = make_float4((rv.x - s.x) * inv_noise, (rv.y - s.y) * inv_noise, (rv.z - s.z) * inv_noise, (rv.w - s.w) * inv_noise);
+    reinterpret_cast<float4*>(Z)[r * 4 + cg] = z;
+    acc.x = fmaf(z.x, rv.x, acc.x); acc.y = fmaf(z.y, rv.y, acc.y); acc.z = fmaf(z.z, rv.z, acc.z); acc.w = fmaf(z.w, rv.w, acc.w);
   }
-  __syncthreads();
-  red[rs * TP + c] = zr;
-  __syncthreads();
-  for (int s = 8; s > 0; s >>= 1) {
-    if (rs < s) red[rs * TP + c] += red[(rs + s) * TP + c];
-    __syncthreads();
-  }
-  if (tid < TP) part[(size_t)blockIdx.x * TP + tid] = red[tid];
+  block_reduce_cols(acc, red, part + (size_t)blockIdx.x * TP);
 }
 
 // partial = sum A.B per column (A, B [n][16])
@@ -415,8 +450,8 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   CgState* S = p->state.as<CgState>();
   const int* done = &S->done;
   const float inv_noise = 1.f / p->noise;
-  const size_t sh_qtr = sizeof(float) * (32 * (size_t)k + 32 * TP);
-  const size_t sh_pre = sizeof(float) * ((size_t)k * TP + 16 * (size_t)k + 16 * TP);
+  const size_t sh_qtr = sizeof(float) * std::max<size_t>(32 * (size_t)((k + 3) & ~3) + 32 * TP, 128 * TP);
+  const size_t sh_pre = sizeof(float) * ((((size_t)k * TP + 3) & ~(size_t)3) + CG_ROWS * TP);
   if (precond && sh_pre > 48 * 1024) {
     GP_CUDA(cudaFuncSetAttribute(cg_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pre));
   }

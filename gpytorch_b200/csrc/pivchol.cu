@@ -226,21 +226,41 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
   }
 }
 
-// W[r][:] = solve(C, L[:, r])  (forward substitution, fp64, one thread per row; C in smem)
-__global__ void wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
-                              const double* __restrict__ C, float* __restrict__ W) {
+// Cinv = C^{-1} (lower triangular, fp64): one thread per column, forward substitution against C in shared memory
+__global__ void cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
   extern __shared__ double Cs[];  // [k][k]
   for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cs[e] = C[e];
   __syncthreads();
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_local) return;
-  double w[128];
-  for (int a = 0; a < k; ++a) {
-    double s = (double)Lt[(int64_t)a * n_total + row_begin + r];
-    for (int b = 0; b < a; ++b) s -= Cs[a * k + b] * w[b];
-    w[a] = s / Cs[a * k + a];
+  const int j = threadIdx.x;
+  if (j >= k) return;
+  for (int i = 0; i < k; ++i) {
+    double s = (i == j) ? 1.0 : 0.0;
+    for (int b = j; b < i; ++b) s -= Cs[i * k + b] * Cinv[(size_t)b * k + j];
+    Cinv[(size_t)i * k + j] = (i < j) ? 0.0 : s / Cs[i * k + i];
   }
-  for (int a = 0; a < k; ++a) W[r * k + a] = (float)w[a];
+}
+
+// W[r][a] = sum_{b<=a} Cinv[a][b] L[b][r]   (W = L C^{-T}); 32 rows x 4 interleaved a-groups per CTA, fp64 accumulate
+__global__ void __launch_bounds__(128)
+wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
+              const double* __restrict__ Cinv, float* __restrict__ W) {
+  extern __shared__ double shw[];
+  double* Ci = shw;                                            // [k][k]
+  float* Ls = reinterpret_cast<float*>(shw + (size_t)k * k);   // [k][32]
+  for (int e = threadIdx.x; e < k * k; e += 128) Ci[e] = Cinv[e];
+  const int rl = threadIdx.x & 31, ag = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  for (int e = threadIdx.x; e < k * 32; e += 128) {
+    int b = e >> 5, rr = e & 31;
+    Ls[e] = (r0 + rr < n_local) ? Lt[(int64_t)b * n_total + row_begin + r0 + rr] : 0.f;
+  }
+  __syncthreads();
+  const int64_t r = r0 + rl;
+  for (int a = ag; a < k; a += 4) {
+    double s = 0.0;
+    for (int b = 0; b <= a; ++b) s = fma(Ci[a * k + b], (double)Ls[b * 32 + rl], s);
+    if (r < n_local) W[r * k + a] = (float)s;
+  }
 }
 
 // Z[r][c] = sum_a L[a][r] eps1[a][c] + sigma eps2[r][c]
@@ -321,9 +341,10 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
   const int nz = (int)std::min<int64_t>(16, std::max<int64_t>(1, n / 4096));
   const int64_t jslice = cdiv(cdiv(n, nz), 64) * 64;
   GP_CHECK(p->gram.ensure(sizeof(double) * (size_t)nz * k * k));
-  GP_CHECK(p->cholC.ensure(sizeof(double) * (size_t)k * k + 64));
+  GP_CHECK(p->cholC.ensure(sizeof(double) * (size_t)2 * k * k + 64));
   double* C = p->cholC.as<double>();
-  double* d_logdet = C + (size_t)k * k;
+  double* Cinv = C + (size_t)k * k;
+  double* d_logdet = Cinv + (size_t)k * k;
   int* d_fail = reinterpret_cast<int*>(d_logdet + 1);
   GP_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
   dim3 gg((unsigned)cdiv(k, 16), (unsigned)cdiv(k, 16), (unsigned)nz);
@@ -332,8 +353,10 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
   GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, (double)p->noise, n, C, d_logdet, d_fail);
-  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 128), 128, shc, st>>>(Lt, k, n, p->row_begin, p->row_count, C, W);
-  p->launches += 3;
+  GP_CUDA(cudaFuncSetAttribute(cinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  cinv_kernel<<<1, 128, shc, st>>>(C, k, Cinv);
+  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32), 128, shc + sizeof(float) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin, p->row_count, Cinv, W);
+  p->launches += 4;
   GP_CUDA(cudaGetLastError());
   double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(p->pinned) + 3072);
   GP_CUDA(cudaMemcpyAsync(h, d_logdet, sizeof(double) + sizeof(int), cudaMemcpyDeviceToHost, st));
