@@ -109,22 +109,23 @@ pc_step_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict_
   __threadfence();
   // ---- last CTA: fixed-order reduction of the partials, stop rule, next pivot ----
   best = -INFINITY; best_pos = 0x7fffffff; asum = 0.0;
-  for (int b = tid; b < (int)gridDim.x; b += PC_THREADS) {
+  for (int b = tid; b < (int)gridDim.x; b += PC_THREADS) {   // fixed assignment + fixed tree => deterministic
     float v2 = ((volatile float*)pval)[b]; int p2 = ((volatile int*)ppos)[b];
     if (v2 > best || (v2 == best && p2 < best_pos)) { best = v2; best_pos = p2; }
+    asum += ((volatile double*)psum)[b];
   }
-  s_val[tid] = best; s_pos[tid] = best_pos;
+  s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
   __syncthreads();
   for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
     if (tid < s) {
       float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
       if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
+      s_sum[tid] += s_sum[tid + s];
     }
     __syncthreads();
   }
   if (tid == 0) {
-    double tot = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) tot += ((volatile double*)psum)[b];
+    const double tot = s_sum[0];
     st->counter = 0;
     st->rank = m + 1;
     const float err = (float)(tot / (double)st->orig_err);

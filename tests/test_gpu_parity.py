@@ -370,6 +370,39 @@ def test_c2_mll_full_size_is_consistent(c2, cuda_dev):
     assert res2.inv_quad == res.inv_quad and res2.logdet == res.logdet
 
 
+def test_c4_batch_of_independent_problems(Plan, cuda_dev):
+    """BASELINE config 4 (batched exact GP, independent hyper-parameters per batch element) runs as one plan per batch
+    element (the batch dimension of the path, not the Kronecker structure); sizes reduced so the
+    fp64 oracle finishes in seconds."""
+    b, n, d = 4, 2400, 8
+    g = torch.Generator().manual_seed(4)
+    for i in range(b):
+        x = torch.rand(n, d, generator=g)
+        y = torch.sin(2 * x.sum(-1)) + 0.1 * torch.randn(n, generator=g)
+        ls, osc, nz = 0.8 + 0.2 * i, 1.0 + 0.5 * i, 0.05 * (i + 1)
+        pn = om.make_probe_noise(n, 40, 10, 10 + i)
+        ro = om.mll_bbmm("rbf", x.double(), y.double(), 0.0, ls, osc, nz, tuple(a.double() for a in pn), precond_size=40)
+        p = Plan(x.to(cuda_dev)).set_hypers("rbf", ls, osc, nz)
+        res, _ = p.mll(y.to(cuda_dev), pn[0].to(cuda_dev), pn[1].to(cuda_dev), pn[2].to(cuda_dev), 10, 40, 2000)
+        assert res.cg_iters == ro.iters
+        assert res.mll == pytest.approx(ro.mll, rel=2e-4)
+        p.close()
+
+
+def test_c1_small_problem_through_cg_path(Plan, cuda_dev):
+    """BASELINE config 1 (N=1000, d=3): below min_preconditioning_size -> Rademacher probes, plain mBCG."""
+    n = 1000
+    x, y = om.synthetic_problem(n, 3, 0, torch.float32)
+    pn = om.make_probe_noise(n, 15, 10, 1)
+    r32 = om.mll_bbmm("rbf", x, y, 0.0, 0.5, 1.0, 0.1, pn)
+    for backend in BACKENDS:
+        p = Plan(x.to(cuda_dev), backend=backend).set_hypers("rbf", 0.5, 1.0, 0.1)
+        res, _ = p.mll(y.to(cuda_dev), pn[0].to(cuda_dev), pn[1].to(cuda_dev), pn[2].to(cuda_dev), 10, 15, 2000)
+        assert res.cg_iters == r32.iters == 21 and res.precond_rank == 0 and res.tridiag_size == 20
+        assert res.mll == pytest.approx(r32.mll, rel=2e-2)
+        p.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the gpytorch-style public API end to end
 # ---------------------------------------------------------------------------------------------------------
