@@ -236,6 +236,28 @@ def test_mbcg_zero_rhs_column_and_not_converged_warning(Plan, cuda_dev):
     p.close()
 
 
+def test_nan_in_matmul_raises_like_the_reference(Plan, cuda_dev):
+    # linear_cg: "NaNs encountered when trying to perform matrix-vector multiplication" (RuntimeError)
+    n = 1500
+    x, y = om.synthetic_problem(n, 3, 0, torch.float32)
+    x[17, 1] = float("nan")
+    p = Plan(x.to(cuda_dev)).set_hypers("rbf", 0.5, 1.0, 0.1)
+    with pytest.raises(RuntimeError, match="NaNs encountered"):
+        p.mbcg(torch.randn(n, 2).to(cuda_dev), 0, 1.0, 50, 20, None)
+    p.close()
+
+
+def test_bad_hyperparameters_are_rejected(Plan, cuda_dev):
+    p = Plan(torch.rand(100, 2).to(cuda_dev))
+    with pytest.raises(RuntimeError, match="positive"):
+        p.set_hypers("rbf", -1.0, 1.0, 0.1)
+    with pytest.raises(RuntimeError, match="does not match"):
+        p.set_hypers("rbf", [1.0, 2.0, 3.0], 1.0, 0.1)
+    with pytest.raises(KeyError):
+        p.set_hypers("periodic", 1.0, 1.0, 0.1)
+    p.close()
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("n,d,kind,ls,rank", [(3000, 10, "rbf", 1.0, 100), (2500, 6, "matern52", 1.0, 30), (2200, 4, "matern12", 0.7, 20)])
 def test_mll_matches_oracle_and_cholesky(Plan, cuda_dev, backend, n, d, kind, ls, rank):
