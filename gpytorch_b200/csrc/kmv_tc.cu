@@ -6,23 +6,24 @@
 //   dense K @ V inside linear_cg         lazy/lazy_evaluated_kernel_tensor.py:245-276 (chunked form)
 // The N x N matrix K never exists in HBM: per 128 x 96 tile it lives in TMEM only.
 //
-// One CTA (352 threads) owns one work unit = (128-row tile of K) x (a contiguous range of 64-column tiles).
-// Per column tile u (TMEM stage u % 4):
+// One CTA (192 threads; TWO CTAs are resident per SM) owns one work unit = (128-row tile of K) x (a contiguous range of
+// 64-column tiles).  Per column tile u (TMEM slot u % 2):
 //   GEMM1  S  = A_i . B_j^T            tcgen05.mma kind::tf32, M=128 N=64 K=KP (3xTF32 split operands packed by pack.cu so
-//                                      that S_ij = -0.5|z_i - z_j|^2 directly); runs a tile ahead of the epilogue
-//   EPI    P  = cov(S)                 two epilogue warpgroups alternate tiles: tcgen05.ld (prefetched) -> ex2/sqrt (MUFU)
-//                                      -> P_hi/P_lo (RN tf32 split) -> tcgen05.st, P_hi IN PLACE of S, P_lo next to it
+//                                      that S_ij = -0.5|z_i - z_j|^2 directly); issued one tile ahead of the epilogue
+//   EPI    P  = cov(S)                 the epilogue warpgroup: tcgen05.ld (chunk 1 prefetched behind chunk 0) -> ex2/sqrt
+//                                      (MUFU) -> P_hi (tf32, IN PLACE of S) + P_lo (bf16 pairs) -> tcgen05.st
 //   GEMM2  O  = P_hi [V_hi;V_lo] (tf32, N=32) + P_lo V (bf16 x bf16, N=16)   A operand from TMEM, B = V^T tiles in smem;
 //          O is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps
 // Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact UMMA
-// K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue WG0, 4-7 epilogue WG1, 8 TMA
-// producer, 9 TMEM allocator + GEMM1 issuer, 10/11 GEMM2 issuers of WG0/WG1 (converged warps, one elect.sync per batch).
-// Measured on B200 (tools/umma_bench.cu, tools/tc_trace.py): a TS-mode MMA costs N/2 cycles (N=16: 8.7), an SS-mode one
-// ~48 at N=64; the issuing thread blocks while its MMAs execute (shallow queue) and an mbarrier wait costs ~90 cycles, so
-// GEMM1 and GEMM2 are issued from different warps and no warp waits in the middle of a tile.
+// K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue, 4 TMA producer, 5 TMEM allocator +
+// MMA issuer (converged warp, one elect.sync per batch; GEMM2(u) then GEMM1(u+2) from the same thread => pipe-ordered).
+// Why two small CTAs per SM instead of one CTA with two epilogue warpgroups (measured, tools/tc_trace.py and
+// profiles/NOTES_r01.md): two warpgroups inside one CTA fall into lockstep on their shared barriers, and the MUFU phase of
+// both then serialises with the tensor phase of both; independent CTAs de-synchronise naturally and fill each other's
+// MUFU / tensor bubbles.  Measured costs that shaped the issue path: a TS-mode MMA = N/2 cycles, an SS-mode one ~48 at
+// N=64, the issuing thread blocks while its MMAs execute, an mbarrier hand-off costs 100-400 cycles.
 //
-// TMEM columns (512 allocated): stage s in {0..3}: [s*96, +64) S -> P_hi (tf32), [s*96+64, +32) P_lo (bf16 pairs) |
-//                               [384,416) O of WG0 | [416,448) O of WG1
+// TMEM columns (256 per CTA): S / P_hi slots [0,64) [64,128) | P_lo slots [128,160) [160,192) | O [192,224)
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,13 +31,13 @@ namespace gp {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 384;  // 8 epilogue warps + producer + GEMM1 issuer + two GEMM2 issuers
-// TMEM columns (512 allocated): NSTG stages of [S -> P_hi (tf32) in place | P_lo (bf16, 2 per column)], then one O
-// accumulator per warpgroup
-constexpr int NSTG = 4;
-constexpr int COL_STAGE = TILE_J + TILE_J / 2; // stage s: S / P_hi at s*96 (64 columns), P_lo at s*96 + 64 (32 columns)
-constexpr int COL_O = NSTG * COL_STAGE;        // O of warpgroup g at COL_O + g*32
-static_assert(TILE_J == 64 && COL_O + 64 <= 512, "TMEM budget is laid out for TILE_J = 64");
+constexpr int TC_THREADS = 192;  // 4 epilogue warps + TMA producer + MMA issuer; TWO such CTAs are resident per SM
+// TMEM columns (256 allocated per CTA; two CTAs share the SM's 512)
+constexpr int NSTG = 2;                         // S / P_hi slots (64 columns each): tile u lives in slot u % 2
+constexpr int COL_LO = NSTG * TILE_J;           // 128: P_lo slot u % 2 at COL_LO + (u % 2) * 32 (bf16 pairs)
+constexpr int COL_O = COL_LO + NSTG * (TILE_J / 2);  // 192: O accumulator (32 columns)
+constexpr int TMEM_COLS = 256;
+static_assert(TILE_J == 64 && COL_O + 2 * TP <= TMEM_COLS, "TMEM budget is laid out for TILE_J = 64");
 constexpr int V_TF32_BYTES = 2 * TILE_J * TP * 4;  // [64/4][32 rows: V_hi(16) | V_lo(16)][4 tf32] = 8192
 constexpr int V_BF16_BYTES = TILE_J * TP * 2;      // [64/8][16 rows][8 bf16]                       = 2048
 constexpr int V_TILE_BYTES = V_TF32_BYTES + V_BF16_BYTES;
@@ -47,9 +48,8 @@ struct TcBars {
   uint64_t b_full[MAX_NS];
   uint64_t b_empty[MAX_NS];
   uint64_t s_full[NSTG];
-  uint64_t g2_done[NSTG];   // GEMM2 finished reading stage s: GEMM1 may overwrite it
-  uint64_t p_full[2];
-  uint64_t o_full[2];
+  uint64_t p_full;
+  uint64_t o_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -59,13 +59,7 @@ struct TcBars {
 //   points, where it is < 2e-6, i.e. k <= 1 + 1.4e-6 -- inside the stated entry tolerance; dropping the FMNMX relieves the
 //   ALU pipe (second-busiest after the XU pipe).  The exact diagonal is still forced to a = 0 in diagonal tiles.
 template <int KIND>
-__device__ __forceinline__ void process_chunk(uint32_t (&r)[32], bool diag_tile, int cd, uint32_t t_hi, uint32_t t_lo) {
-  uint32_t lo[16];
-  if (diag_tile) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c == cd) r[c] = 0u;  // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
-  }
+__device__ __forceinline__ void cov_split_32(uint32_t (&r)[32], uint32_t* lo) {
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
     float p0, p1;
@@ -84,17 +78,33 @@ __device__ __forceinline__ void process_chunk(uint32_t (&r)[32], bool diag_tile,
     r[c] = h0;
     r[c + 1] = h1;
   }
-  GP_TMEM_ST32(t_hi, r);
-  GP_TMEM_ST16(t_lo, lo);
+}
+// the whole 64-column tile of one thread in ONE basic block: 64 independent ex2 / split chains give the scheduler a
+// window deep enough to keep the XU pipe fed (per-chunk store barriers serialised the two halves), then 4 stores.
+template <int KIND>
+__device__ __forceinline__ void process_tile(uint32_t (&ra)[32], uint32_t (&rb)[32], bool diag_tile, int cd, uint32_t t_hi, uint32_t t_lo) {
+  uint32_t lo[32];
+  if (diag_tile) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c == cd) ra[c] = 0u;        // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
+      if (c + 32 == cd) rb[c] = 0u;
+    }
+  }
+  cov_split_32<KIND>(ra, lo);
+  cov_split_32<KIND>(rb, lo + 16);
+  GP_TMEM_ST32(t_hi, ra);
+  GP_TMEM_ST32(t_hi + 32, rb);
+  GP_TMEM_ST32(t_lo, lo);
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const float* __restrict__ Vt,
               float* __restrict__ partial, int KP, int NS, int64_t ntile_j, int64_t tiles_per_split,
               int64_t rows_pad, int same, int64_t row_begin, const int* __restrict__ done_flag, long long* __restrict__ trace) {
   if (done_flag && *done_flag) return;  // CTA-uniform, before any barrier / TMEM state exists
-  // optional event trace of CTA (0,0): trace[tile][8] = {g1_issue, g2_issue, wg_sfull_wait, wg_sfull_done, wg_c0_done, wg_ofull_done, wg_tile_end, -}
+  // optional event trace of CTA (0,0): trace[tile][8] = {g1_issue, g2_issue, sfull_wait, sfull_done, c0_done, ofull_done, tile_end, -}
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 #define GP_TR(tile, ev) do { if (tr && lane == 0 && (tile) < 256) trace[(tile) * 8 + (ev)] = clock64(); } while (0)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -119,23 +129,18 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       mbar_init(smem_u32(&bars->b_full[s]), 1);
       mbar_init(smem_u32(&bars->b_empty[s]), 1);
     }
-    for (int s = 0; s < NSTG; ++s) {
-      mbar_init(smem_u32(&bars->s_full[s]), 1);
-      mbar_init(smem_u32(&bars->g2_done[s]), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->p_full[s]), 128);
-      mbar_init(smem_u32(&bars->o_full[s]), 1);
-    }
+    for (int s = 0; s < NSTG; ++s) mbar_init(smem_u32(&bars->s_full[s]), 1);
+    mbar_init(smem_u32(&bars->p_full), 128);
+    mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  if (warp == 5) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ===================== TMA producer (one lane) =====================
     if (lane == 0 && T > 0) {
       mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
@@ -153,29 +158,33 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         if (++sb == NS) { sb = 0; par ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ===================== GEMM1 issuer (converged warp, one elected lane issues each batch) ==========
-    // GEMM1 runs ahead of the epilogue through the 3 TMEM stages; it only waits for smem tiles and for GEMM2 to have
-    // drained the stage it is about to overwrite (tile u-3).
+  } else if (warp == 5) {
+    // ===================== MMA issuer (converged warp, one elected lane issues each batch) ==========
+    // Program order per tile u:  wait P(u) -> GEMM2(u) -> GEMM1(u+2) into the slot GEMM2(u) has just read.  One thread
+    // issues both, so the tensor pipe orders them and no "slot drained" barrier is needed; GEMM1 runs one tile ahead of
+    // the epilogue, whose math overlaps GEMM2(u-1) + GEMM1(u+1).
     if (T > 0) {
-      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);   // S = A B^T   128 x 64
+      constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);    // S = A B^T                       128 x 64
+      constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);   // O  = P_hi [V_hi;V_lo]^T  (tf32) 128 x 32
+      constexpr uint32_t IDESC2B = idesc_bf16(TILE_I, TP);       // O += P_lo V^T            (bf16) 128 x 16
       const int ksteps1 = KP / 8;
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), TILE_I * 16, 128);
+      const uint32_t d_o = tmem + (uint32_t)COL_O;
       mbar_wait(smem_u32(&bars->a_full), 0);
-      int sb1 = 0;
+      int sb1 = 0;          // smem ring slot of the next GEMM1
       uint32_t par1 = 0;
-      for (int u = 0; u < T; ++u) {
-        const int slot = u % NSTG, use = u / NSTG;
+      int g1 = 0;           // next tile GEMM1 produces
+      auto issue_g1 = [&]() {
+        const int slot = g1 % NSTG;
         mbar_wait(smem_u32(&bars->b_full[sb1]), par1);
-        if (use > 0) mbar_wait(smem_u32(&bars->g2_done[slot]), (uint32_t)((use - 1) & 1));
         tc_fence_after();
-        GP_TR(u, 0);
+        GP_TR(g1, 0);
         const uint64_t b_desc0 = smem_desc(smem_u32(sStage + (size_t)sb1 * stage_bytes), TILE_J * 16, 128);
-        const uint32_t d_s = tmem + (uint32_t)(slot * COL_STAGE);
+        const uint32_t d_s = tmem + (uint32_t)(slot * TILE_J);
         const uint32_t sfull = smem_u32(&bars->s_full[slot]);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KP_MAX / 8; ++ks)  // fully unrolled + predicated: keeps every operand in uniform registers
+          for (int ks = 0; ks < KP_MAX / 8; ++ks)  // fully unrolled + predicated: every operand stays in uniform registers
             if (ks < ksteps1)
               mma_tf32_ss_1t(d_s, a_desc0 + (uint64_t)(ks * ((2 * TILE_I * 16) >> 4)), b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)),
                              IDESC1, ks > 0 ? 1u : 0u);
@@ -183,78 +192,67 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         }
         __syncwarp();
         if (++sb1 == NS) { sb1 = 0; par1 ^= 1; }
+        ++g1;
+      };
+      issue_g1();
+      if (T > 1) issue_g1();
+      int sb2 = 0;
+      for (int u = 0; u < T; ++u) {
+        const int slot = u % NSTG;
+        mbar_wait(smem_u32(&bars->p_full), (uint32_t)(u & 1));
+        tc_fence_after();
+        GP_TR(u, 1);
+        const uint32_t v_addr = smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes);
+        const uint64_t v_desc0 = smem_desc(v_addr, 2 * TP * 16, 128);                 // tf32 tile, 32 rows
+        const uint64_t w_desc0 = smem_desc(v_addr + V_TF32_BYTES, TP * 16, 128);      // bf16 tile, 16 rows
+        const uint32_t p_hi = tmem + (uint32_t)(slot * TILE_J);
+        const uint32_t p_lo = tmem + (uint32_t)(COL_LO + slot * (TILE_J / 2));
+        const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < TILE_J / 8; ++ks)
+            mma_tf32_ts_1t(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < TILE_J / 16; ++ks)
+            mma_bf16_ts_1t(d_o, p_lo + ks * 8, w_desc0 + (uint64_t)(ks * ((2 * TP * 16) >> 4)), IDESC2B, 1u);
+          tc_commit_1t(bempty);   // smem slot (B + V) is free again
+          tc_commit_1t(ofull);    // O holds tile u's product
+        }
+        __syncwarp();
+        if (++sb2 == NS) sb2 = 0;
+        if (g1 < T) issue_g1();   // refill the TMEM slot GEMM2(u) has just consumed (same thread => ordered)
       }
     }
-  } else if (warp >= 10) {
-    // ===================== GEMM2 issuers: warp 10 serves warpgroup 0's tiles (even u), warp 11 warpgroup 1's ==========
-    // O[g] = P_hi [V_hi;V_lo]^T (tf32, N=32) + P_lo V^T (bf16 x bf16, N=16); a fresh accumulator per tile.
-    const int g = warp - 10;
-    constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, 2 * TP);
-    constexpr uint32_t IDESC2B = idesc_bf16(TILE_I, TP);
-    const uint32_t d_o = tmem + (uint32_t)(COL_O + g * 2 * TP);
-    int sb2 = g % NS;
-    for (int u = g; u < T; u += 2) {
-      const int stage = u % NSTG;
-      mbar_wait(smem_u32(&bars->p_full[g]), (uint32_t)((u >> 1) & 1));
-      tc_fence_after();
-      GP_TR(u, 1);
-      const uint32_t v_addr = smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes);
-      const uint64_t v_desc0 = smem_desc(v_addr, 2 * TP * 16, 128);                 // tf32 tile, 32 rows
-      const uint64_t w_desc0 = smem_desc(v_addr + V_TF32_BYTES, TP * 16, 128);      // bf16 tile, 16 rows
-      const uint32_t p_hi = tmem + (uint32_t)(stage * COL_STAGE);
-      const uint32_t p_lo = p_hi + TILE_J;
-      const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full[g]),
-                     g2d = smem_u32(&bars->g2_done[stage]);
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < TILE_J / 8; ++ks)
-          mma_tf32_ts_1t(d_o, p_hi + ks * 8, v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4)), IDESC2A, ks > 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < TILE_J / 16; ++ks)
-          mma_bf16_ts_1t(d_o, p_lo + ks * 8, w_desc0 + (uint64_t)(ks * ((2 * TP * 16) >> 4)), IDESC2B, 1u);
-        tc_commit_1t(bempty);   // smem slot (B + V) is free again
-        tc_commit_1t(ofull);    // O[g] holds tile u's product
-        tc_commit_1t(g2d);      // TMEM stage may be refilled by GEMM1(u + NSTG)
-      }
-      __syncwarp();
-      sb2 += 2;
-      while (sb2 >= NS) sb2 -= NS;
-    }
-  } else if (warp < 8) {
-    // ===================== epilogue warpgroups =====================
-    const int wg = warp >> 2;          // 0 or 1: handles tiles u = wg, wg+2, ...
+  } else {
+    // ===================== epilogue warpgroup (warps 0-3) =====================
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int64_t gi = row_begin + it * TILE_I + q * 32 + lane;  // global row of this thread
-    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * 2 * TP);
+    const uint32_t t_o = tmem + lane_off + (uint32_t)COL_O;
     // O is folded into fp32 registers after EVERY tile: the tensor core's accumulator truncates on each add, so long
-    // TMEM accumulation chains drift (1e-4 at N = 50k); 16 adds per tile keep the product at fp32 level.
+    // TMEM accumulation chains drift (1e-4 at N = 50k); 12 adds per tile keep the product at fp32 level.
     float acc[TP];
 #pragma unroll
     for (int c = 0; c < TP; ++c) acc[c] = 0.f;
-    int npend = 0;  // 1 when the previous tile's O has not been folded into acc yet
-    for (int u = wg; u < T; u += 2) {
-      const int stage = u % NSTG;
+    for (int u = 0; u < T; ++u) {
+      const int slot = u % NSTG;
       if (q == 0) GP_TR(u, 2);
-      mbar_wait(smem_u32(&bars->s_full[stage]), (uint32_t)((u / NSTG) & 1));
+      mbar_wait(smem_u32(&bars->s_full[slot]), (uint32_t)((u / NSTG) & 1));
       tc_fence_after();
       if (q == 0) GP_TR(u, 3);
-      const uint32_t t_s = tmem + lane_off + (uint32_t)(stage * COL_STAGE);   // S, overwritten in place by P_hi
-      const uint32_t t_lo = t_s + TILE_J;
+      const uint32_t t_s = tmem + lane_off + (uint32_t)(slot * TILE_J);   // S, overwritten in place by P_hi
+      const uint32_t t_lo = tmem + lane_off + (uint32_t)(COL_LO + slot * (TILE_J / 2));
       const int64_t jbase = (jt0 + u) * TILE_J;
       const bool diag_tile = same && (row_begin + it * TILE_I < jbase + TILE_J) && (jbase < row_begin + (it + 1) * TILE_I);
-      // two 32-column chunks in two register sets: chunk 1 is loaded behind the math of chunk 0 (no copies)
       uint32_t ra[32], rb[32];
       GP_TMEM_LD32(t_s, ra);
-      tmem_wait_ld();
       GP_TMEM_LD32(t_s + 32, rb);
-      process_chunk<KIND>(ra, diag_tile, (int)(gi - jbase), t_s, t_lo);
-      if (q == 0) GP_TR(u, 4);
       tmem_wait_ld();
-      process_chunk<KIND>(rb, diag_tile, (int)(gi - (jbase + 32)), t_s + 32, t_lo + 16);
-      if (npend) {
-        // GEMM2(u-2) was issued a whole tile ago: its O is complete; fold it before GEMM2(u) overwrites O[wg]
-        mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)(((u - 2) >> 1) & 1));
+      process_tile<KIND>(ra, rb, diag_tile, (int)(gi - jbase), t_s, t_lo);
+      if (q == 0) GP_TR(u, 4);
+      if (u >= 1) {
+        // GEMM2(u-1) was issued when this tile started: its O is complete by now; fold it before GEMM2(u) overwrites O
+        mbar_wait(smem_u32(&bars->o_full), (uint32_t)((u - 1) & 1));
         tc_fence_after();
         uint32_t o[32];
         GP_TMEM_LD32(t_o, o);
@@ -263,15 +261,13 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
         if (q == 0) GP_TR(u, 5);
       }
-      npend = 1;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[wg]));  // GEMM2(u) may now read P (this stage) and overwrite O[wg]
+      mbar_arrive(smem_u32(&bars->p_full));  // GEMM2(u) may now read P (this slot) and overwrite O
       if (q == 0) GP_TR(u, 6);
     }
-    if (npend) {
-      const int ulast = wg + 2 * ((T - 1 - wg) / 2);
-      mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)((ulast >> 1) & 1));
+    if (T > 0) {
+      mbar_wait(smem_u32(&bars->o_full), (uint32_t)((T - 1) & 1));
       tc_fence_after();
       uint32_t o[32];
       GP_TMEM_LD32(t_o, o);
@@ -279,25 +275,29 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
 #pragma unroll
       for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
     }
-    // each warpgroup owns one partial slot: partial[split * 2 + wg][row][16]
     const int64_t row = it * TILE_I + q * 32 + lane;
-    float4* dst = reinterpret_cast<float4*>(partial + (((int64_t)split * 2 + wg) * rows_pad + row) * TP);
+    float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + row) * TP);
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
 static int tc_smem_bytes(int KP, int* ns_out) {
   const int a_bytes = KP * TILE_I * 4;
   const int stage = KP * TILE_J * 4 + V_TILE_BYTES;
-  const int budget = 220 * 1024 - a_bytes - (int)sizeof(TcBars) - 1024;
+  // preferred: two CTAs per SM (<= ~112 KB each); wide feature vectors fall back to one CTA per SM
+  int budget = 112 * 1024 - a_bytes - (int)sizeof(TcBars) - 1024;
   int ns = budget / stage;
+  if (ns < 3) {
+    budget = 220 * 1024 - a_bytes - (int)sizeof(TcBars) - 1024;
+    ns = budget / stage;
+  }
   if (ns > MAX_NS) ns = MAX_NS;
   *ns_out = ns;
   return a_bytes + ns * stage + (int)sizeof(TcBars) + 64;

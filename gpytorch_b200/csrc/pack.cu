@@ -155,8 +155,9 @@ int choose_geometry(gp_plan* p) {
     int64_t per = cdiv(ntj, s);
     if (s > 1 && per < 8) break;  // keep units long enough to amortise the prologue
     int64_t units = nti * s;
-    int64_t waves = cdiv(units, p->n_sm);
-    double eff = (double)(nti * ntj) / (double)(waves * p->n_sm * per);
+    const int64_t slots = (int64_t)p->n_sm * (p->backend == GP_BACKEND_TCGEN05 ? 2 : 1);  // resident CTAs
+    int64_t waves = cdiv(units, slots);
+    double eff = (double)(nti * ntj) / (double)(waves * slots * per);
     if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
   }
   p->tiles_per_split = cdiv(ntj, best);
@@ -211,7 +212,7 @@ int pack_inputs(gp_plan* p) {
     GP_CHECK(p->Vtiles.ensure(sizeof(float) * p->ntile_j * (2 * TILE_J * TP + TILE_J * TP / 2)));
   }
   int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
-  p->nparts = p->nsplit * (p->backend == GP_BACKEND_TCGEN05 ? 2 : 1);  // tcgen05: one slot per epilogue warpgroup
+  p->nparts = p->nsplit;
   GP_CHECK(p->partial.ensure(sizeof(float) * (size_t)p->nparts * rows_pad * TP));
   GP_CUDA(cudaGetLastError());
   return GP_OK;
