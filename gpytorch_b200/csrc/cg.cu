@@ -246,13 +246,14 @@ __global__ void cg_initdir_kernel(const float* __restrict__ Z, float* __restrict
 // V = os * sum_s partial + noise * P ; partial pv = sum P.V
 __global__ void cg_finishv_kernel(const float* __restrict__ kpart, int nsplit, int64_t rows_pad, float os, float noise,
                                   const float* __restrict__ P, float* __restrict__ V, int64_t n, float* __restrict__ part,
-                                  const int* done) {
+                                  const int* done, const int* __restrict__ xbad) {
   if (done && *done) return;
   __shared__ __align__(16) float red[CG_ROWS * TP];
   const int tid = threadIdx.x, cg = tid & 3, rl = tid >> 2;
+  const float poison = *xbad ? __int_as_float(0x7fc00000) : 0.f;  // non-finite inputs: K.V is NaN in the reference
   float4 acc = make_float4(0, 0, 0, 0);
   for (int64_t r = (int64_t)blockIdx.x * CG_ROWS + rl; r < n; r += (int64_t)gridDim.x * CG_ROWS) {
-    float4 s = make_float4(0, 0, 0, 0);
+    float4 s = make_float4(poison, poison, poison, poison);
     for (int sp = 0; sp < nsplit; ++sp) {
       float4 a = reinterpret_cast<const float4*>(kpart)[((int64_t)sp * rows_pad + r) * 4 + cg];
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
@@ -495,7 +496,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   for (kk = 0; kk < max_iter && !finished; ++kk) {
     status = kmv_partials(p, Pfull, done);
     if (status != GP_OK) break;
-    cg_finishv_kernel<<<G, CG_THREADS, 0, st>>>(p->partial.as<float>(), p->nparts, rows_pad, p->outputscale, p->noise, P, V, n, red, done);
+    cg_finishv_kernel<<<G, CG_THREADS, 0, st>>>(p->partial.as<float>(), p->nparts, rows_pad, p->outputscale, p->noise, P, V, n, red, done, p->xbad);
     cg_sum_kernel<<<1, 256, 0, st>>>(red, G, TP, sums_a, done);
     if ((status = allreduce(p, sums_a, TP)) != GP_OK) break;
     cg_update_kernel<<<G, CG_THREADS, 0, st>>>(sums_a, kk, eps, P, V, U, R, n, S, red, L2);

@@ -127,6 +127,7 @@ struct gp_plan {
   int nparts = 1;  // partial-sum slots written by the K.V kernel (nsplit, x2 for the tcgen05 kernel)
   int64_t ntile_i = 0, ntile_j = 0, tiles_per_split = 0;
   // device buffers
+  int* xbad = nullptr;  // device flag: non-finite value in the packed inputs (lives behind mean[])
   gp::DevBuf mean, scale, Z1, Z2, XA, XB, V16, Vtiles, partial, out16;
   gp::DevBuf cgU, cgR, cgZ, cgP, cgV, cgPfull, red, sums, qtr, state, tmat_tmp, misc, misc2, misc3;
   gp::DevBuf pcdiag, pcperm, pcpos, pcstate, gram, cholC;

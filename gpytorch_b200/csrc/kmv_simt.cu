@@ -115,7 +115,7 @@ int kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
 // OUT[r, c] = os * sum_s partial[s][r][c] + noise * V16[row_begin + r][c]
 __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int nsplit, int64_t rows, int64_t rows_pad,
                                        float os, float noise_add, const float* __restrict__ V16, int64_t row_begin,
-                                       float* __restrict__ OUT, int64_t ldo, int t) {
+                                       float* __restrict__ OUT, int64_t ldo, int t, const int* __restrict__ xbad) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * TP) return;
   int64_t r = idx / TP;
@@ -125,6 +125,7 @@ __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int ns
   for (int sp = 0; sp < nsplit; ++sp) s += partial[((int64_t)sp * rows_pad + r) * TP + c];
   float o = os * s;
   if (noise_add != 0.f) o = fmaf(noise_add, V16[(row_begin + r) * TP + c], o);
+  if (*xbad) o = __int_as_float(0x7fc00000);
   OUT[r * ldo + c] = o;
 }
 
@@ -134,7 +135,7 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
   float na = (add_noise && p->same) ? p->noise : 0.f;
   kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count,
                                                                           rows_pad, p->outputscale, na, V16, p->row_begin,
-                                                                          OUT, ldo, t);
+                                                                          OUT, ldo, t, p->xbad);
   p->launches++;
   GP_CUDA(cudaGetLastError());
   return GP_OK;

@@ -110,7 +110,7 @@ extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol
   };
   auto reorth = [&](int m) {  // r -= Q[:m] (Q[:m]^T r)
     lz_gemv_t_kernel<<<m, 256, 0, st>>>(Qt, n, r, cvec);
-    lz_gemv_n_kernel<<<G, 256, sizeof(float) * m, st>>>(Qt, m, n, cvec, r);
+    lz_gemv_n_kernel<<<G, 256, sizeof(float) * ((m + 3) & ~3), st>>>(Qt, m, n, cvec, r);
     p->launches += 2;
   };
 

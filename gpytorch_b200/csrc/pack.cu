@@ -33,12 +33,16 @@ __global__ void col_mean_kernel(const float* __restrict__ X, int64_t n, int64_t 
 
 __global__ void pack_simt_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int d, int DP,
                                  const float* __restrict__ mean, const float* __restrict__ scale,
-                                 float* __restrict__ Z) {
+                                 float* __restrict__ Z, int* __restrict__ xbad) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * DP) return;
   int64_t r = idx / DP;
   int c = (int)(idx % DP);
-  Z[idx] = (c < d) ? (X[r * ld + c] - mean[c]) * scale[c] : 0.f;
+  float z = (c < d) ? (X[r * ld + c] - mean[c]) * scale[c] : 0.f;
+  Z[idx] = z;
+  // a NaN/Inf anywhere in the inputs makes every entry of K (hence of K.V) NaN in the reference (mean-centring in
+  // kernels/kernel.py:35-37 spreads it); the covariance code clamps with fmin/fmax, which would swallow it, so record it
+  if (!(fabsf(z) <= 3.402823466e38f)) *xbad = 1;
 }
 
 // one thread per (padded) row; writes KP floats as KP/4 float4 (coalesced across rows)
@@ -170,7 +174,9 @@ int pack_inputs(gp_plan* p) {
   GP_CHECK(choose_geometry(p));
   cudaStream_t st = p->stream;
   const int d = p->d, DP = p->DP;
-  GP_CHECK(p->mean.ensure(sizeof(float) * d));
+  GP_CHECK(p->mean.ensure(sizeof(float) * (d + 4)));
+  p->xbad = reinterpret_cast<int*>(p->mean.as<float>() + d);
+  GP_CUDA(cudaMemsetAsync(p->xbad, 0, sizeof(int), st));
   GP_CHECK(p->scale.ensure(sizeof(float) * d));
   // scale_c = sqrt(const) / l_c
   std::vector<float> sc(d);
@@ -189,14 +195,14 @@ int pack_inputs(gp_plan* p) {
   {
     int64_t tot = p->n2 * DP;
     pack_simt_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(X2, p->n2, ld2, d, DP, p->mean.as<float>(),
-                                                              p->scale.as<float>(), p->Z2.as<float>());
+                                                              p->scale.as<float>(), p->Z2.as<float>(), p->xbad);
     p->launches++;
   }
   if (!p->same) {
     GP_CHECK(p->Z1.ensure(sizeof(float) * p->row_count * DP));
     int64_t tot = p->row_count * DP;
     pack_simt_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(p->X1 + p->row_begin * p->ld1, p->row_count, p->ld1, d, DP,
-                                                              p->mean.as<float>(), p->scale.as<float>(), p->Z1.as<float>());
+                                                              p->mean.as<float>(), p->scale.as<float>(), p->Z1.as<float>(), p->xbad);
     p->launches++;
   }
   if (p->backend == GP_BACKEND_TCGEN05) {
