@@ -11,7 +11,7 @@ import os
 import warnings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpbbmm.so")
+LIB_PATH = os.environ.get("GPBBMM_LIB") or os.path.join(_HERE, "lib", "libgpbbmm.so")   # GPBBMM_LIB: see INTEGRATION.md
 
 GP_OK, GP_E_SHAPE, GP_E_CUDA, GP_E_NAN_MVM, GP_W_NOT_CONVERGED, GP_W_PIVCHOL_NAN, GP_E_NCCL, GP_E_STATE = range(8)
 GP_RBF, GP_MATERN12, GP_MATERN32, GP_MATERN52 = range(4)

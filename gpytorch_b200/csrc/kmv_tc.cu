@@ -6,24 +6,28 @@
 //   dense K @ V inside linear_cg         lazy/lazy_evaluated_kernel_tensor.py:245-276 (chunked form)
 // The N x N matrix K never exists in HBM: per 128 x 96 tile it lives in TMEM only.
 //
-// One CTA (192 threads; TWO CTAs are resident per SM) owns one work unit = (128-row tile of K) x (a contiguous range of
-// 64-column tiles).  Per column tile u (TMEM slot u % 2):
+// One CTA (320 threads; TWO CTAs are resident per SM) owns one work unit = (128-row tile of K) x (a contiguous range of
+// 64-column tiles).  Per column tile u (TMEM slot u % 2, epilogue warpgroup u % 2):
 //   GEMM1  S  = A_i . B_j^T            tcgen05.mma kind::tf32, M=128 N=64 K=KP (3xTF32 split operands packed by pack.cu so
-//                                      that S_ij = -0.5|z_i - z_j|^2 directly); issued one tile ahead of the epilogue
-//   EPI    P  = cov(S)                 the epilogue warpgroup: tcgen05.ld (chunk 1 prefetched behind chunk 0) -> ex2/sqrt
-//                                      (MUFU) -> P_hi (tf32, IN PLACE of S) + P_lo (bf16 pairs) -> tcgen05.st
+//                                      that S_ij = -0.5|z_i - z_j|^2 directly)
+//   EPI    P  = cov(S)                 software pipeline over 8-column groups: tcgen05.ld (two groups ahead) -> ex2/sqrt
+//                                      (MUFU, one group ahead) -> P_hi (tf32, IN PLACE of S) + P_lo (bf16 pairs) -> tcgen05.st
 //   GEMM2  O  = P_hi [V_hi;V_lo] (tf32, N=32) + P_lo V (bf16 x bf16, N=16)   A operand from TMEM, B = V^T tiles in smem;
-//          O is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps
+//          O[u % 2] is a fresh accumulator per tile, folded into fp32 registers by the epilogue warps two tiles later
 // Operands arrive by bulk TMA (cp.async.bulk, mbarrier complete_tx) from tiles pre-packed in HBM in the exact UMMA
-// K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 epilogue, 4 TMA producer, 5 TMEM allocator +
-// MMA issuer (converged warp, one elect.sync per batch; GEMM2(u) then GEMM1(u+2) from the same thread => pipe-ordered).
-// Why two small CTAs per SM instead of one CTA with two epilogue warpgroups (measured, tools/tc_trace.py and
-// profiles/NOTES_r01.md): two warpgroups inside one CTA fall into lockstep on their shared barriers, and the MUFU phase of
-// both then serialises with the tensor phase of both; independent CTAs de-synchronise naturally and fill each other's
-// MUFU / tensor bubbles.  Measured costs that shaped the issue path: a TS-mode MMA = N/2 cycles, an SS-mode one ~48 at
-// N=64, the issuing thread blocks while its MMAs execute, an mbarrier hand-off costs 100-400 cycles.
+// K-major no-swizzle layout, through a NS-deep smem ring.  Warp roles: 0-3 / 4-7 the two epilogue warpgroups, 8 TMA
+// producer, 9 TMEM allocator + MMA issuer (converged warp, one elect.sync per batch; GEMM2(u) then GEMM1(u+2) from the
+// same thread => pipe-ordered, which is what makes the in-place P safe without a "slot drained" barrier).
 //
-// TMEM columns (256 per CTA): S / P_hi slots [0,64) [64,128) | P_lo slots [128,160) [160,192) | O [192,224)
+// What bounds it (tools/mufu_bench.cu, tools/tc_trace.py, profiles/NOTES_r01.md): the MUFU unit does 16 ex2/clk/SM
+// (measured 15.99), i.e. 512 cycles per 128x64 tile.  TMEM holds 4 tile slots per SM (128 columns each: S/P_hi 64,
+// P_lo 32, O 32), every slot is a dependent chain  GEMM1 -> s_full -> ld -> MUFU -> st -> p_full -> GEMM2 -> GEMM1'
+// with ~1000 cycles of fixed latency (mbarrier hand-offs 100-400 each, SS-mode MMA 48 cycles, queueing in the tensor
+// pipe) and the MUFU phases of all slots share one unit, so the tile time is ~512 + 1000/4 cycles.  Two small CTAs per
+// SM instead of one big one: warpgroups inside one CTA fall into lockstep on shared barriers, independent CTAs do not.
+// Every barrier is private to one slot, so an epilogue warp may run one tile ahead of its siblings.
+//
+// TMEM columns (256 per CTA): S / P_hi slots [0,64) [64,128) | P_lo slots [128,160) [160,192) | O slots [192,224) [224,256)
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -31,13 +35,15 @@ namespace gp {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 192;  // 4 epilogue warps + TMA producer + MMA issuer; TWO such CTAs are resident per SM
+constexpr int TC_THREADS = 320;  // 2 epilogue warpgroups (one per TMEM slot) + TMA producer + MMA issuer; TWO CTAs per SM
+constexpr int W_PROD = 8, W_MMA = 9;
 // TMEM columns (256 allocated per CTA; two CTAs share the SM's 512)
 constexpr int NSTG = 2;                         // S / P_hi slots (64 columns each): tile u lives in slot u % 2
 constexpr int COL_LO = NSTG * TILE_J;           // 128: P_lo slot u % 2 at COL_LO + (u % 2) * 32 (bf16 pairs)
 constexpr int COL_O = COL_LO + NSTG * (TILE_J / 2);  // 192: O accumulator (32 columns)
 constexpr int TMEM_COLS = 256;
-static_assert(TILE_J == 64 && COL_O + 2 * TP <= TMEM_COLS, "TMEM budget is laid out for TILE_J = 64");
+constexpr int NO = 2;                           // O accumulators (32 columns each): tile u accumulates into O[u % 2]
+static_assert(TILE_J == 64 && COL_O + NO * 2 * TP <= TMEM_COLS, "TMEM budget is laid out for TILE_J = 64");
 constexpr int V_TF32_BYTES = 2 * TILE_J * TP * 4;  // [64/4][32 rows: V_hi(16) | V_lo(16)][4 tf32] = 8192
 constexpr int V_BF16_BYTES = TILE_J * TP * 2;      // [64/8][16 rows][8 bf16]                       = 2048
 constexpr int V_TILE_BYTES = V_TF32_BYTES + V_BF16_BYTES;
@@ -48,54 +54,61 @@ struct TcBars {
   uint64_t b_full[MAX_NS];
   uint64_t b_empty[MAX_NS];
   uint64_t s_full[NSTG];
-  uint64_t p_full;
-  uint64_t o_full;
+  uint64_t p_full[NSTG];   // per slot: an epilogue warp may run one tile ahead of its siblings (never two: tile u+2 needs
+                           // GEMM1(u+2), issued after p_full(u) completed), so consecutive tiles must not share a barrier
+  uint64_t o_full[NO];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-// P = cov(S) for 32 columns held in r[], tf32 / bf16 split, store P_hi in place of S and P_lo next to it.
+// P = cov(S), split P = P_hi (tf32, stored in place of S) + P_lo (bf16 pairs), for the 64 columns one thread holds.
 //   RBF: k = 2^a with NO clamp of a at 0: a = -0.5|z_i - z_j|^2 can only come out > 0 through rounding for (near-)duplicate
 //   points, where it is < 2e-6, i.e. k <= 1 + 1.4e-6 -- inside the stated entry tolerance; dropping the FMNMX relieves the
 //   ALU pipe (second-busiest after the XU pipe).  The exact diagonal is still forced to a = 0 in diagonal tiles.
+// The tile is processed as a software pipeline over groups of 8 columns: the MUFU ops of group g+1 are issued BEFORE
+// the split of group g, so that every consumer sits >= 8 MUFU slots (64 pipe cycles) behind its producer -- an in-order
+// warp that reads a MUFU result 2-3 slots after issuing it stalls ~20 cycles each time and lets the XU pipe run dry
+// (measured: one warp alone reached 57 % of the XU rate with the straightforward per-pair loop).
 template <int KIND>
-__device__ __forceinline__ void cov_split_32(uint32_t (&r)[32], uint32_t* lo) {
+__device__ __forceinline__ void cov_group8(const uint32_t* __restrict__ s, float (&p)[8]) {
 #pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    float p0, p1;
-    if (KIND == GP_RBF) {
-      p0 = ex2_approx(__uint_as_float(r[c]));
-      p1 = ex2_approx(__uint_as_float(r[c + 1]));
-    } else {
-      p0 = cov_from_arg<KIND>(__uint_as_float(r[c]));
-      p1 = cov_from_arg<KIND>(__uint_as_float(r[c + 1]));
-    }
-    // tf32 truncation (one LOP3) -- the residual in [0, 2^-10 p) goes to bf16 (RN), two per TMEM column: P is kept to
-    // ~2^-19 relative, random sign
-    uint32_t h0 = __float_as_uint(p0) & 0xFFFFE000u;
-    uint32_t h1 = __float_as_uint(p1) & 0xFFFFE000u;
-    lo[c >> 1] = pack_bf16x2(p0 - __uint_as_float(h0), p1 - __uint_as_float(h1));
-    r[c] = h0;
-    r[c + 1] = h1;
+  for (int i = 0; i < 8; ++i)
+    p[i] = (KIND == GP_RBF) ? ex2_approx(__uint_as_float(s[i])) : cov_from_arg<KIND>(__uint_as_float(s[i]));
+}
+// tf32 truncation (one LOP3 each), residual in [0, 2^-10 p) by one packed FADD2 per pair, rounded to bf16 (RN), two per
+// TMEM column: P is kept to ~2^-19 relative, random sign
+__device__ __forceinline__ void split_group8(const float (&p)[8], uint32_t* __restrict__ hi, uint32_t* __restrict__ lo) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const uint32_t h0 = __float_as_uint(p[i]) & 0xFFFFE000u, h1 = __float_as_uint(p[i + 1]) & 0xFFFFE000u;
+    float l0, l1;
+    sub_f32x2(p[i], p[i + 1], __uint_as_float(h0), __uint_as_float(h1), l0, l1);
+    lo[i >> 1] = pack_bf16x2(l0, l1);
+    hi[i] = h0;
+    hi[i + 1] = h1;
   }
 }
-// the whole 64-column tile of one thread in ONE basic block: 64 independent ex2 / split chains give the scheduler a
-// window deep enough to keep the XU pipe fed (per-chunk store barriers serialised the two halves), then 4 stores.
-template <int KIND>
-__device__ __forceinline__ void process_tile(uint32_t (&ra)[32], uint32_t (&rb)[32], bool diag_tile, int cd, uint32_t t_hi, uint32_t t_lo) {
-  uint32_t lo[32];
-  if (diag_tile) {
+// One step of the pipeline: (1) the S columns of group g+1 (loaded during the previous step) go through the MUFU into
+// pn, (2) the load of group g+2 is put in flight into sn2, (3) group g (MUFU results from the previous step, in pc) is
+// split and stored.  The loop over steps is a REAL loop (not unrolled): ptxas schedules inside one step only, so a MUFU
+// result is never consumed in the step that issued it.
+template <int KIND, bool HAS_NEXT, bool HAS_NEXT2>
+__device__ __forceinline__ void epi_step(int g, uint32_t t_hi, uint32_t t_lo, const float (&pc)[8], uint32_t (&sn)[8], float (&pn)[8],
+                                         uint32_t (&sn2)[8], bool diag_tile, int cd) {
+  if (HAS_NEXT) {
+    tmem_wait_ld();                                      // sn = S columns of group g+1 has arrived
+    if (diag_tile) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      if (c == cd) ra[c] = 0u;        // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
-      if (c + 32 == cd) rb[c] = 0u;
+      for (int i = 0; i < 8; ++i)
+        if (8 * (g + 1) + i == cd) sn[i] = 0u;           // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
     }
   }
-  cov_split_32<KIND>(ra, lo);
-  cov_split_32<KIND>(rb, lo + 16);
-  GP_TMEM_ST32(t_hi, ra);
-  GP_TMEM_ST32(t_hi + 32, rb);
-  GP_TMEM_ST32(t_lo, lo);
+  if (HAS_NEXT2) GP_TMEM_LD8(t_hi + 8 * (g + 2), sn2);
+  if (HAS_NEXT) cov_group8<KIND>(sn, pn);
+  uint32_t hi[8], lo[4];
+  split_group8(pc, hi, lo);
+  GP_TMEM_ST8(t_hi + 8 * g, hi);
+  GP_TMEM_ST4(t_lo + 4 * g, lo);
 }
 
 template <int KIND>
@@ -130,17 +143,17 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       mbar_init(smem_u32(&bars->b_empty[s]), 1);
     }
     for (int s = 0; s < NSTG; ++s) mbar_init(smem_u32(&bars->s_full[s]), 1);
-    mbar_init(smem_u32(&bars->p_full), 128);
-    mbar_init(smem_u32(&bars->o_full), 1);
+    for (int i = 0; i < NSTG; ++i) mbar_init(smem_u32(&bars->p_full[i]), 128);
+    for (int i = 0; i < NO; ++i) mbar_init(smem_u32(&bars->o_full[i]), 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+  if (warp == W_MMA) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == W_PROD) {
     // ===================== TMA producer (one lane) =====================
     if (lane == 0 && T > 0) {
       mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
@@ -158,7 +171,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         if (++sb == NS) { sb = 0; par ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer (converged warp, one elected lane issues each batch) ==========
     // Program order per tile u:  wait P(u) -> GEMM2(u) -> GEMM1(u+2) into the slot GEMM2(u) has just read.  One thread
     // issues both, so the tensor pipe orders them and no "slot drained" barrier is needed; GEMM1 runs one tile ahead of
@@ -169,7 +182,6 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       constexpr uint32_t IDESC2B = idesc_bf16(TILE_I, TP);       // O += P_lo V^T            (bf16) 128 x 16
       const int ksteps1 = KP / 8;
       const uint64_t a_desc0 = smem_desc(smem_u32(sA), TILE_I * 16, 128);
-      const uint32_t d_o = tmem + (uint32_t)COL_O;
       mbar_wait(smem_u32(&bars->a_full), 0);
       int sb1 = 0;          // smem ring slot of the next GEMM1
       uint32_t par1 = 0;
@@ -199,7 +211,7 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       int sb2 = 0;
       for (int u = 0; u < T; ++u) {
         const int slot = u % NSTG;
-        mbar_wait(smem_u32(&bars->p_full), (uint32_t)(u & 1));
+        mbar_wait(smem_u32(&bars->p_full[slot]), (uint32_t)((u / NSTG) & 1));
         tc_fence_after();
         GP_TR(u, 1);
         const uint32_t v_addr = smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes);
@@ -207,7 +219,8 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
         const uint64_t w_desc0 = smem_desc(v_addr + V_TF32_BYTES, TP * 16, 128);      // bf16 tile, 16 rows
         const uint32_t p_hi = tmem + (uint32_t)(slot * TILE_J);
         const uint32_t p_lo = tmem + (uint32_t)(COL_LO + slot * (TILE_J / 2));
-        const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full);
+        const uint32_t bempty = smem_u32(&bars->b_empty[sb2]), ofull = smem_u32(&bars->o_full[u % NO]);
+        const uint32_t d_o = tmem + (uint32_t)(COL_O + (u % NO) * 2 * TP);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < TILE_J / 8; ++ks)
@@ -224,7 +237,8 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       }
     }
   } else {
-    // ===================== epilogue warpgroup (warps 0-3) =====================
+    // ===================== epilogue warpgroups (warps 0-3: even tiles / slot 0, warps 4-7: odd tiles / slot 1) =========
+    const int wg = warp >> 2;
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int64_t gi = row_begin + it * TILE_I + q * 32 + lane;  // global row of this thread
@@ -234,8 +248,8 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
     float acc[TP];
 #pragma unroll
     for (int c = 0; c < TP; ++c) acc[c] = 0.f;
-    for (int u = 0; u < T; ++u) {
-      const int slot = u % NSTG;
+    for (int u = wg; u < T; u += 2) {
+      const int slot = wg;
       if (q == 0) GP_TR(u, 2);
       mbar_wait(smem_u32(&bars->s_full[slot]), (uint32_t)((u / NSTG) & 1));
       tc_fence_after();
@@ -244,45 +258,84 @@ kmv_tc_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const 
       const uint32_t t_lo = tmem + lane_off + (uint32_t)(COL_LO + slot * (TILE_J / 2));
       const int64_t jbase = (jt0 + u) * TILE_J;
       const bool diag_tile = same && (row_begin + it * TILE_I < jbase + TILE_J) && (jbase < row_begin + (it + 1) * TILE_I);
-      uint32_t ra[32], rb[32];
-      GP_TMEM_LD32(t_s, ra);
-      GP_TMEM_LD32(t_s + 32, rb);
-      tmem_wait_ld();
-      process_tile<KIND>(ra, rb, diag_tile, (int)(gi - jbase), t_s, t_lo);
-      if (q == 0) GP_TR(u, 4);
-      if (u >= 1) {
-        // GEMM2(u-1) was issued when this tile started: its O is complete by now; fold it before GEMM2(u) overwrites O
-        mbar_wait(smem_u32(&bars->o_full), (uint32_t)((u - 1) & 1));
-        tc_fence_after();
+      const int cd = (int)(gi - jbase);
+      uint32_t sa[8], sb[8];
+      float pa[8], pb[8];
+      GP_TMEM_LD8(t_s, sa);
+      GP_TMEM_LD8(t_s + 8, sb);
+      if (u >= 2) {
+        // fold O(u-2): its TMEM load rides with the first S loads and its adds are scheduled into the MUFU-bound steps.
+        // No o_full wait: s_full(u) was committed by the issuer thread AFTER it issued GEMM2(u-2), and tcgen05.commit tracks
+        // all prior MMAs of that thread.  O[u % 2] is next written by GEMM2(u), issued after this thread's arrive on
+        // p_full(u).  (Waiting for GEMM2(u-1) instead, issued only when THIS tile started, costs ~500 cycles.)
         uint32_t o[32];
-        GP_TMEM_LD32(t_o, o);
+        GP_TMEM_LD32(t_o + (uint32_t)((u % NO) * 2 * TP), o);
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
-        if (q == 0) GP_TR(u, 5);
+      } else {
+        tmem_wait_ld();
       }
+      if (diag_tile) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i == cd) sa[i] = 0u;
+      }
+      cov_group8<KIND>(sa, pa);                          // group 0 in pa; group 1's S in sb
+      if (q == 0) GP_TR(u, 4);
+#pragma unroll 1
+      for (int g = 0; g < 6; g += 2) {
+        epi_step<KIND, true, true>(g, t_s, t_lo, pa, sb, pb, sa, diag_tile, cd);      // MUFU g+1 -> pb, load g+2 -> sa, split g
+        epi_step<KIND, true, true>(g + 1, t_s, t_lo, pb, sa, pa, sb, diag_tile, cd);  // MUFU g+2 -> pa, load g+3 -> sb, split g+1
+      }
+      epi_step<KIND, true, false>(6, t_s, t_lo, pa, sb, pb, sa, diag_tile, cd);
+      epi_step<KIND, false, false>(7, t_s, t_lo, pb, sa, pa, sb, diag_tile, cd);
+      if (q == 0) GP_TR(u, 5);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full));  // GEMM2(u) may now read P (this slot) and overwrite O
+      mbar_arrive(smem_u32(&bars->p_full[slot]));  // GEMM2(u) may now read P (this slot); it accumulates into O[u % 2]
       if (q == 0) GP_TR(u, 6);
     }
-    if (T > 0) {
-      mbar_wait(smem_u32(&bars->o_full), (uint32_t)((T - 1) & 1));
-      tc_fence_after();
-      uint32_t o[32];
-      GP_TMEM_LD32(t_o, o);
-      tmem_wait_ld();
+    {
+      const int w = ((T - 1 - wg) >= 0) ? (T - 1 - ((T - 1 - wg) & 1)) : -1;   // this warpgroup's last tile: still in TMEM
+      if (w >= 0) {
+        mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)((w / NO) & 1));
+        tc_fence_after();
+        uint32_t o[32];
+        GP_TMEM_LD32(t_o + (uint32_t)(wg * 2 * TP), o);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
+        for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]) + __uint_as_float(o[TP + c]);
+      }
     }
+    // combine the two warpgroups' partial sums through smem.  The exchange buffer reuses ring slot 0, so the OTHER
+    // warpgroup's last GEMM2 (which may still be reading its B / V stage) must have completed too.
+    {
+      const int og = wg ^ 1;
+      const int wo = ((T - 1 - og) >= 0) ? (T - 1 - ((T - 1 - og) & 1)) : -1;
+      if (wo >= 0) mbar_wait(smem_u32(&bars->o_full[og]), (uint32_t)((wo / NO) & 1));
+    }
+    float* xch = reinterpret_cast<float*>(sStage);
+    const int rloc = q * 32 + lane;
+    if (wg == 1) {
+#pragma unroll
+      for (int c = 0; c < TP; ++c) xch[c * TILE_I + rloc] = acc[c];
+    }
+    named_bar_sync(1, 256);
+    if (wg == 0) {
+#pragma unroll
+      for (int c = 0; c < TP; ++c) acc[c] += xch[c * TILE_I + rloc];
+    }
+    if (wg == 0) {
     const int64_t row = it * TILE_I + q * 32 + lane;
     float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + row) * TP);
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }

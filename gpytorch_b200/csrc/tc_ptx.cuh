@@ -159,6 +159,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // {upper, lower} = {bf16(hi_elem), bf16(lo_elem)}: the LOWER half is the even (lower-k) element of a packed TMEM column
+// (a0, a1) - (b0, b1) as ONE packed fp32x2 instruction (FADD2, sm_100)
+__device__ __forceinline__ void sub_f32x2(float a0, float a1, float b0, float b1, float& d0, float& d1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lower, float upper) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
@@ -204,6 +212,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lower, float upper) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                      \
       : "r"(taddr)                                                                                                    \
       : "memory")
+
+#define GP_TMEM_LD8(taddr, r)                                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                          \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])           \
+               : "r"(taddr)                                                                                              \
+               : "memory")
+#define GP_TMEM_ST8(taddr, r)                                                                                         \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),  \
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                               \
+               : "memory")
+#define GP_TMEM_ST4(taddr, r)                                                                                         \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),       \
+               "r"(r[2]), "r"(r[3])                                                                                      \
+               : "memory")
 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

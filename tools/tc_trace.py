@@ -17,7 +17,7 @@ p.kmv(v); torch.cuda.synchronize()
 p.lib.gp_plan_set_trace(p._h, None)
 t = tr.cpu().view(256, 8)
 t0 = int(t[0, 0])
-names = ["g1_issue", "g2_issue", "sfull_wait", "sfull_done", "c0_done", "ofull_done", "tile_end"]
+names = ["g1_issue", "g2_issue", "sfull_wait", "sfull_done", "ld_fold", "math_done", "tile_end"]
 print("tile " + " ".join(f"{n_:>10s}" for n_ in names))
 for u in range(0, 60):
     print(f"{u:4d} " + " ".join(f"{int(t[u, e]) - t0 if int(t[u, e]) else -1:10d}" for e in range(7)))
