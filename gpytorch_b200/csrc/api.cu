@@ -239,6 +239,14 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   const int64_t n = p->row_count, N = p->n2;
   const int tp = o->num_probes, t = tp + 1;
   int flags = 0;
+  // GP_MLL_TIMING=1: CUDA-event time of every phase, printed to stderr (profiling aid; adds event records only)
+  const bool timing = getenv("GP_MLL_TIMING") != nullptr;
+  cudaEvent_t tev[8];
+  int ntev = 0;
+  auto mark = [&]() {
+    if (timing && ntev < 8) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev], st); ++ntev; }
+  };
+  mark();
 
   // --- preconditioner (AddedDiagLinearOperator._preconditioner) ---
   int k = 0;
@@ -265,6 +273,7 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   }
   res->precond_rank = k;
   res->logdet_precond = logdet_p;
+  mark();
 
   // --- probes and the [Z | y - mu] right-hand side ---
   GP_CHECK(p->misc3.ensure(sizeof(float) * (size_t)n * (tp + t + t) + sizeof(float) * (size_t)tp * o->max_tridiag_iter * o->max_tridiag_iter + 4096));
@@ -287,6 +296,7 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
     concat_rhs_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(pz, tp, y_minus_mean, n, rhs, nullptr);
     p->launches++;
   }
+  mark();
   // linear_cg normalises every column itself (probe_vector_norms only matter for the backward pass), so the
   // un-normalised probes give the same solves for the y column and the same tridiagonals.
   int iters = 0, J = 0;
@@ -295,6 +305,7 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   else GP_CHECK(st_cg);
   res->cg_iters = iters;
   res->tridiag_size = J;
+  mark();
 
   double logdet = 0.0;
   GP_CHECK(gp_slq_logdet(p, tmat, tp, o->max_tridiag_iter, J, N, &logdet));
@@ -309,6 +320,19 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   GP_CUDA(cudaStreamSynchronize(st));
   double iq = 0.0;
   for (int i = 0; i < 64; ++i) iq += h[i];
+  if (timing) {
+    mark();
+    cudaEventSynchronize(tev[ntev - 1]);
+    static const char* names[] = {"pivchol+precond_build", "probes+rhs", "mbcg", "slq+invquad"};
+    fprintf(stderr, "[gp_mll timing]");
+    for (int i = 0; i + 1 < ntev; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      fprintf(stderr, " %s %.3f ms;", names[i], ms);
+    }
+    fprintf(stderr, " cg_iters %d\n", iters);
+    for (int i = 0; i < ntev; ++i) cudaEventDestroy(tev[i]);
+  }
   if (p->comm && p->comm->world > 1) {
     // inv_quad is a sum over local rows: all-reduce it (one fp64)
     double* d_iq = iq_part;

@@ -143,6 +143,7 @@ int pack_inputs(gp_plan* p);                                            // pack.
 int to_v16(gp_plan* p, const float* V, int64_t ldv, int t, int64_t n, float* V16);
 int pack_v_tiles(gp_plan* p, const float* V16);                         // pack.cu (tcgen05 B operand of GEMM2)
 int kmv_partials(gp_plan* p, const float* V16, const int* done_flag);   // dispatch simt / tcgen05
+int kmv_tc_launch_kind(gp_plan* p, int kind, const int* done_flag);     // kind may be GP_DERIV + kind
 int kmv_simt_launch(gp_plan* p, const float* V16, const int* done_flag);
 int kmv_tc_launch(gp_plan* p, const int* done_flag);
 int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t, int add_noise);
@@ -169,9 +170,20 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__fl
 // covariance from a = -0.5 |z_i - z_j|^2 in the pre-scaled units of pack.cu:
 //   RBF     z = (x - mean) sqrt(log2 e) / l      k = 2^a                (rbf_covariance.py:19)
 //   Matern  z = (x - mean) sqrt(4 nu) / l        rho^2 = -a = 2 nu r^2  (matern_covariance.py:21-47)
+// internal "derivative kinds": the same tile loop evaluates g = l dk/dl (scalar lengthscale) instead of k, so that
+// the bilinear derivative  sum_ij (L_i . R_j) g_ij = sum_i L_i . (G R)_i  is one more fused K.V launch
+// (lazy_evaluated_kernel_tensor.py:69-105, functions/rbf_covariance.py:20-29, functions/matern_covariance.py:27-56)
+constexpr int GP_DERIV = 4;   // GP_DERIV + kind
+
+template <int KIND>
+__device__ __forceinline__ float dcov_from_arg(float a, float* kout);
+
 template <int KIND>
 __device__ __forceinline__ float cov_from_arg(float a) {
-  if (KIND == GP_RBF) {
+  if (KIND >= GP_DERIV) {
+    float k;
+    return dcov_from_arg<KIND - GP_DERIV>(a, &k);
+  } else if (KIND == GP_RBF) {
     return ex2_approx(fminf(a, 0.f));
   } else {
     float rho = sqrt_approx(fmaxf(-a, 0.f));

@@ -258,6 +258,25 @@ __global__ void sum_partials_double_kernel(const double* __restrict__ in, int64_
   out[o] = s;
 }
 
+// tcgen05 path of the bilinear derivative: gout[block][o] = sum_{r,c} L16[r][c] * sum_split partial[split][r][c]
+__global__ void bilin_dot_kernel(const float* __restrict__ partial, int nsplit, int64_t rows, int64_t rows_pad,
+                                 const float* __restrict__ L16, double* __restrict__ gout, int gstride, int o) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < rows * TP; e += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[(int64_t)sp * rows_pad * TP + e];
+    acc += (double)L16[e] * (double)s;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int sft = 128; sft > 0; sft >>= 1) {
+    if (threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gout[(int64_t)blockIdx.x * gstride + o] = red[0];
+}
+
 template <int KIND, bool ARD>
 static int launch_bilinear(gp_plan* p, const float* L16, const float* R16, double* gout, int gstride, dim3 grid, int64_t cps) {
   const float* Z1 = p->same ? p->Z2.as<float>() + p->row_begin * p->DP : p->Z1.as<float>();
@@ -328,10 +347,33 @@ extern "C" int gp_bilinear_grad(gp_plan* p, const float* Lf, int64_t ldl, const 
   GP_CHECK(p->misc3.ensure(sizeof(float) * p->n2 * TP));
   double* gout = p->misc.as<double>();
   double* gsum = gout + nblk * nout;
+  // scalar lengthscale on the tensor-core backend: sum_ij (L_i . R_j) f_ij = sum_i L_i . (F R)_i, i.e. two launches of
+  // the fused K.V kernel (f = k, then f = g = l dk/dl through the derivative kinds) + a dot product with L.  ARD needs d
+  // weighted sums per pair and stays on the SIMT kernel.
+  const bool use_tc = !ard && p->backend == GP_BACKEND_TCGEN05;
+  const int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
+  const int dot_blocks = (int)std::min<int64_t>(nblk, 2 * p->n_sm);
   for (int c0 = 0; c0 < s; c0 += TP) {
     int tc = std::min(TP, s - c0);
     GP_CHECK(to_v16(p, Lf + c0, ldl, tc, p->row_count, p->misc2.as<float>()));
     GP_CHECK(to_v16(p, Rt + c0, ldr, tc, p->n2, p->misc3.as<float>()));
+    if (use_tc) {
+      GP_CHECK(pack_v_tiles(p, p->misc3.as<float>()));
+      for (int pass = 0; pass < 2; ++pass) {
+        GP_CHECK(kmv_tc_launch_kind(p, pass == 0 ? p->kind : GP_DERIV + p->kind, nullptr));
+        bilin_dot_kernel<<<dot_blocks, 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count, rows_pad,
+                                                            p->misc2.as<float>(), gout, nout, pass);
+        p->launches++;
+      }
+      GP_CUDA(cudaGetLastError());
+      sum_partials_double_kernel<<<(unsigned)cdiv(nout, 64), 64, 0, p->stream>>>(gout, dot_blocks, nout, nout, gsum);
+      p->launches++;
+      std::vector<double> h(nout);
+      GP_CUDA(cudaMemcpyAsync(h.data(), gsum, sizeof(double) * nout, cudaMemcpyDeviceToHost, p->stream));
+      GP_CUDA(cudaStreamSynchronize(p->stream));
+      for (int o = 0; o < nout; ++o) total[o] += h[o];
+      continue;
+    }
     int st;
 #define GP_BL_KIND(KK)                                                                                         \
   st = ard ? launch_bilinear<KK, true>(p, p->misc2.as<float>(), p->misc3.as<float>(), gout, nout, grid, cps)   \

@@ -361,7 +361,7 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   int ns = 0;
   int smem_bytes = tc_smem_bytes(p->KP, &ns);
   GP_REQUIRE(ns >= 3, GP_E_SHAPE, "tcgen05 path: smem ring too small for KP=%d", p->KP);
-  static bool attr_done[4] = {false, false, false, false};
+  static bool attr_done[2 * GP_DERIV] = {};
   if (!attr_done[KIND]) {
     GP_CUDA(cudaFuncSetAttribute(kmv_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[KIND] = true;
@@ -376,15 +376,20 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   return GP_OK;
 }
 
-int kmv_tc_launch(gp_plan* p, const int* done_flag) {
-  switch (p->kind) {
+int kmv_tc_launch_kind(gp_plan* p, int kind, const int* done_flag) {
+  switch (kind) {
     case GP_RBF: return launch_tc_kind<GP_RBF>(p, done_flag);
     case GP_MATERN12: return launch_tc_kind<GP_MATERN12>(p, done_flag);
     case GP_MATERN32: return launch_tc_kind<GP_MATERN32>(p, done_flag);
     case GP_MATERN52: return launch_tc_kind<GP_MATERN52>(p, done_flag);
+    case GP_DERIV + GP_RBF: return launch_tc_kind<GP_DERIV + GP_RBF>(p, done_flag);
+    case GP_DERIV + GP_MATERN12: return launch_tc_kind<GP_DERIV + GP_MATERN12>(p, done_flag);
+    case GP_DERIV + GP_MATERN32: return launch_tc_kind<GP_DERIV + GP_MATERN32>(p, done_flag);
+    case GP_DERIV + GP_MATERN52: return launch_tc_kind<GP_DERIV + GP_MATERN52>(p, done_flag);
   }
-  set_error("bad kernel kind %d", p->kind);
+  set_error("bad kernel kind %d", kind);
   return GP_E_SHAPE;
 }
+int kmv_tc_launch(gp_plan* p, const int* done_flag) { return kmv_tc_launch_kind(p, p->kind, done_flag); }
 
 }  // namespace gp

@@ -20,7 +20,8 @@ struct PcState {
   float dpiv;      // sqrt(max diag) = L[m][pivot]
   float orig_err;  // max of the initial diagonal
   float err;
-  unsigned int counter;  // last-block-done ticket
+  unsigned int counter;  // last-block-done ticket (step-wise path)
+  unsigned int bar;      // monotonic grid-barrier counter (persistent path)
 };
 
 constexpr int PC_THREADS = 128;
@@ -150,13 +151,163 @@ pc_step_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict_
   }
 }
 
+// ---- persistent variant: ALL steps in one cooperative launch -----------------------------------------------------------
+// The step-wise path above pays a kernel launch + a last-CTA hand-off (~20 us) per step for ~2 us of work.  Here the
+// grid stays resident (cudaLaunchCooperativeKernel guarantees co-residency), every thread owns the same rows in every
+// step, and the steps are separated by two grid barriers: (A) partials written -> CTA 0 reduces them, applies the stop
+// rule and the permutation swap; (B) state published -> next step.  Arithmetic per entry is identical to pc_step_kernel.
+__device__ __forceinline__ void pc_grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*((volatile unsigned int*)bar) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PC_THREADS)
+pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, int64_t n, int max_rank, float tol,
+                     float* diag, int* perm, int* pos, PcState* st, int64_t* piv_out, float* pval, int* ppos, double* psum) {
+  extern __shared__ float sh[];
+  float* zp = sh;           // [DP]
+  float* lp = sh + DP;      // [max_rank]   L[q][pivot]
+  float* col = lp + max_rank;  // [max_rank][PC_THREADS]: L[q][j] of this thread's FIRST row (the dot product below is
+                               // latency bound on L2 when it re-reads the column from Lt: 1.4 ms -> per 100 steps)
+  __shared__ float s_val[PC_THREADS];
+  __shared__ int s_pos[PC_THREADS];
+  __shared__ double s_sum[PC_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * PC_THREADS;
+  const int64_t jfirst = (int64_t)blockIdx.x * PC_THREADS + tid;
+  unsigned int nbar = 0;
+  for (int m = 0; m < max_rank; ++m) {
+    const int pi = *((volatile int*)&st->pivot);
+    const float dpiv = *((volatile float*)&st->dpiv);
+    for (int c = tid; c < DP; c += PC_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+    for (int q = tid; q < m; q += PC_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM
+    __syncthreads();
+    float best = -INFINITY;
+    int best_pos = 0x7fffffff;
+    double asum = 0.0;
+    float* Lm = Lt + (int64_t)m * n;
+    for (int64_t j = (int64_t)blockIdx.x * PC_THREADS + tid; j < n; j += stride) {
+      const int pj = __ldcg(pos + j);
+      const bool cached = (j == jfirst);
+      if (pj < m) {
+        Lm[j] = 0.f;
+        if (cached) col[m * PC_THREADS + tid] = 0.f;
+      } else if (pj == m) {
+        Lm[j] = dpiv;
+        if (cached) col[m * PC_THREADS + tid] = dpiv;
+      } else {
+        float s = 0.f;
+        for (int c = 0; c < DP; ++c) {
+          float df = zp[c] - Z[j * DP + c];
+          s = fmaf(df, df, s);
+        }
+        float v = os * cov_from_arg<KIND>(-0.5f * s);
+        {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int q = 0;
+          if (cached) {   // same values, same order as the global-memory branch: bit-identical
+            const float* cj = col + tid;
+            for (; q + 4 <= m; q += 4) {
+              s0 = fmaf(lp[q], cj[q * PC_THREADS], s0);
+              s1 = fmaf(lp[q + 1], cj[(q + 1) * PC_THREADS], s1);
+              s2 = fmaf(lp[q + 2], cj[(q + 2) * PC_THREADS], s2);
+              s3 = fmaf(lp[q + 3], cj[(q + 3) * PC_THREADS], s3);
+            }
+            for (; q < m; ++q) s0 = fmaf(lp[q], cj[q * PC_THREADS], s0);
+          } else {
+            for (; q + 4 <= m; q += 4) {
+              s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);          // column j is only ever written by this thread
+              s1 = fmaf(lp[q + 1], Lt[(int64_t)(q + 1) * n + j], s1);
+              s2 = fmaf(lp[q + 2], Lt[(int64_t)(q + 2) * n + j], s2);
+              s3 = fmaf(lp[q + 3], Lt[(int64_t)(q + 3) * n + j], s3);
+            }
+            for (; q < m; ++q) s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
+          }
+          v -= (s0 + s1) + (s2 + s3);
+        }
+        v /= dpiv;
+        Lm[j] = v;
+        if (cached) col[m * PC_THREADS + tid] = v;
+        const float dn = diag[j] - v * v;
+        diag[j] = dn;
+        float cv; int cp;
+        if (dn != dn) { cv = INFINITY; cp = -1; }  // NaN poisons the selection
+        else { cv = dn; cp = pj; }
+        if (cv > best || (cv == best && cp < best_pos)) { best = cv; best_pos = cp; }
+        asum += fabs((double)dn);
+      }
+    }
+    s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
+    __syncthreads();
+    for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+        float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
+        if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
+        s_sum[tid] += s_sum[tid + s];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { pval[blockIdx.x] = s_val[0]; ppos[blockIdx.x] = s_pos[0]; psum[blockIdx.x] = s_sum[0]; }
+    pc_grid_barrier(&st->bar, (++nbar) * gridDim.x);   // (A) all partials are visible
+    if (blockIdx.x == 0) {
+      best = -INFINITY; best_pos = 0x7fffffff; asum = 0.0;
+      for (int b = tid; b < (int)gridDim.x; b += PC_THREADS) {   // fixed assignment + fixed tree => deterministic
+        float v2 = __ldcg(pval + b); int p2 = __ldcg(ppos + b);
+        if (v2 > best || (v2 == best && p2 < best_pos)) { best = v2; best_pos = p2; }
+        asum += __ldcg(psum + b);
+      }
+      s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
+      __syncthreads();
+      for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+          float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
+          if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
+          s_sum[tid] += s_sum[tid + s];
+        }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const double tot = s_sum[0];
+        st->rank = m + 1;
+        const float err = (float)(tot / (double)st->orig_err);
+        st->err = err;
+        const float mx = s_val[0];
+        const int pp = s_pos[0];
+        if (m + 1 >= max_rank || (int64_t)(m + 1) >= n || !(err > tol)) {
+          st->done = 1;
+        } else if (pp < 0 || !(mx > 0.f)) {
+          st->nan_flag = 1;
+          st->done = 1;
+        } else {
+          const int pi_new = perm[pp];
+          const int pi_old = perm[m + 1];
+          perm[m + 1] = pi_new; perm[pp] = pi_old;
+          pos[pi_new] = m + 1; pos[pi_old] = pp;
+          st->pivot = pi_new;
+          st->dpiv = sqrtf(mx);
+          piv_out[m + 1] = (int64_t)pi_new;
+        }
+      }
+    }
+    pc_grid_barrier(&st->bar, (++nbar) * gridDim.x);   // (B) state + swap are visible
+    if (*((volatile int*)&st->done)) break;
+  }
+}
+
 __global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, float os,
                                PcState* __restrict__ st, int64_t* __restrict__ piv_out) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     // the initial diagonal of a stationary kernel is constant: torch.max returns the first entry -> pivot 0
     st->done = 0; st->rank = 0; st->pivot = 0; st->nan_flag = (os > 0.f) ? 0 : 1; st->dpiv = sqrtf(os);
-    st->orig_err = os; st->err = 0.f; st->counter = 0u;
+    st->orig_err = os; st->err = 0.f; st->counter = 0u; st->bar = 0u;
     piv_out[0] = 0;
   }
   if (j >= n) return;
@@ -309,6 +460,30 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
   pc_init_kernel<<<gb, PC_THREADS, 0, st>>>(diag, perm, pos, n, p->outputscale, S, piv);
   p->launches += 1;
   const float* Z = p->Z2.as<float>();
+  const bool stepwise = getenv("GP_PC_STEPWISE") != nullptr;   // debugging / A-B switch: one launch per step
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device);
+  if (coop && !stepwise) {
+    const size_t sh = sizeof(float) * (p->DP + rank + (size_t)rank * PC_THREADS);
+    const void* fn;
+    switch (p->kind) {
+      case GP_RBF: fn = (const void*)pc_persistent_kernel<GP_RBF>; break;
+      case GP_MATERN12: fn = (const void*)pc_persistent_kernel<GP_MATERN12>; break;
+      case GP_MATERN32: fn = (const void*)pc_persistent_kernel<GP_MATERN32>; break;
+      default: fn = (const void*)pc_persistent_kernel<GP_MATERN52>; break;
+    }
+    GP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    int per_sm = 0;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PC_THREADS, sh));
+    GP_REQUIRE(per_sm >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
+    const unsigned grid = std::min<unsigned>(gb, (unsigned)(per_sm * p->n_sm));   // gb partial slots are allocated
+    int DPv = p->DP, rk = rank;
+    float osv = p->outputscale, tolv = error_tol;
+    int64_t nn = n;
+    void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &perm, &pos, &S, &piv, &pval, &ppos, &psum};
+    GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PC_THREADS), args, sh, st));
+    p->launches += 1;
+  } else {
   for (int m = 0; m < rank; ++m) {
     size_t sh = sizeof(float) * (p->DP + m);
 #define GP_PC_LAUNCH(KK) pc_step_kernel<KK><<<gb, PC_THREADS, sh, st>>>(Z, p->DP, p->outputscale, Lt, n, m, rank, error_tol, diag, perm, pos, S, piv, pval, ppos, psum)
@@ -320,6 +495,7 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
     }
 #undef GP_PC_LAUNCH
     p->launches += 1;
+  }
   }
   GP_CUDA(cudaGetLastError());
   PcState* hs = reinterpret_cast<PcState*>(reinterpret_cast<char*>(p->pinned) + 2048);

@@ -20,10 +20,11 @@ class ExactGP(Module):
         self.train_targets = train_targets
         self.likelihood = likelihood
         self._mean_cache = None
+        self._covar_cache = None
 
     def train(self, mode=True):
         if mode:
-            self._mean_cache = None  # module.py:351-355: train() clears caches
+            self._mean_cache = self._covar_cache = None  # module.py:351-355: train() clears caches
         return super().train(mode)
 
     def __call__(self, *args, **kwargs):
@@ -49,10 +50,22 @@ class ExactGP(Module):
             k_star = KernelLinearOperator(test_x.contiguous(), train_x, kop.kind, kop.lengthscale, kop.outputscale)
             test_mean = self.mean_module(test_x) + k_star.matmul(self._mean_cache)  # :396
             k_ss = KernelLinearOperator(test_x.contiguous(), None, kop.kind, kop.lengthscale, kop.outputscale)
-            k_xs = KernelLinearOperator(train_x, test_x.contiguous(), kop.kind, kop.lengthscale, kop.outputscale)
-            rhs = k_xs.to_dense()                    # [n, m]
-            corr = k_star.matmul(khat.solve(rhs))    # exact predictive covariance, :431-462
-            covar = k_ss.to_dense() - corr
+            if settings.skip_posterior_variances.on():       # exact_prediction_strategies.py:432-433
+                covar = torch.zeros(test_x.size(0), test_x.size(0), device=test_x.device)
+            elif settings.fast_pred_var.on():                # LOVE: :268-272 (cache), :464-478 (use)
+                if self._covar_cache is None:
+                    init = None
+                    if settings.probe_seed.value() is not None:
+                        g = torch.Generator(device="cpu").manual_seed(int(settings.probe_seed.value()))
+                        init = torch.randn(train_x.size(0), generator=g).to(train_x.device)
+                    self._covar_cache = khat.root_inv_decomposition(init).detach()   # [n, J], R R^T ~= K_hat^{-1}
+                root = k_star.matmul(self._covar_cache)      # covar_inv_quad_form_root, [m, J]
+                covar = k_ss.to_dense() - root @ root.transpose(-1, -2)
+            else:
+                k_xs = KernelLinearOperator(train_x, test_x.contiguous(), kop.kind, kop.lengthscale, kop.outputscale)
+                rhs = k_xs.to_dense()                    # [n, m]
+                corr = k_star.matmul(khat.solve(rhs))    # exact predictive covariance, :435-462
+                covar = k_ss.to_dense() - corr
         return MultivariateNormal(test_mean, covar)
 
     def set_train_data(self, inputs=None, targets=None, strict=True):
@@ -62,4 +75,4 @@ class ExactGP(Module):
             self.train_inputs = tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in inputs)
         if targets is not None:
             self.train_targets = targets
-        self._mean_cache = None
+        self._mean_cache = self._covar_cache = None

@@ -314,8 +314,10 @@ class AddedDiagLinearOperator:
         if init.dim() == 2:
             init = init[:, 0]
         q, t = p.lanczos(init.float(), settings.max_root_decomposition_size.value())
-        evals, evecs = torch.linalg.eigh(t.double())
-        evals = evals.clamp_min(1e-12)
+        evals, evecs = torch.linalg.eigh(t.double())      # J x J, J <= 100: plumbing-sized
+        mask = evals >= 0                                 # lanczos_tridiag_to_diag masks negative Ritz values
+        evecs = evecs * mask
+        evals = evals.masked_fill(~mask, 1.0)
         return (q.double() @ (evecs / evals.sqrt())).float()
 
 

@@ -100,6 +100,17 @@ class skip_logdet_forward(_feature_flag):
     _default = False
 
 
+class fast_pred_var(_feature_flag):
+    """LOVE predictive variances: K_hat^{-1} ~= R R^T from `max_root_decomposition_size` Lanczos steps
+    (settings.py:183-222; models/exact_prediction_strategies.py:268-272, 464-478)."""
+    _default = False
+
+
+class skip_posterior_variances(_feature_flag):
+    """Return a zero predictive covariance (models/exact_prediction_strategies.py:432-433)."""
+    _default = False
+
+
 class _use_eval_tolerance(_feature_flag):
     _default = False
 

@@ -372,3 +372,21 @@ def lanczos_tridiag(matmul_closure, max_iter, init_vecs, tol=1e-5):
     q_out = q_mat[:num_iter].permute(2, 1, 0).contiguous()
     t_out = t_mat[:num_iter, :num_iter].permute(2, 0, 1).contiguous()
     return q_out, t_out
+
+
+def root_inv_decomposition(matmul_closure, max_iter, init_vec, tol=1e-5):
+    """Lanczos root of A^{-1}: R [N, J] with R R^T ~= A^{-1} (linear_operator RootDecomposition, inverse branch, reached
+    from gpytorch/models/exact_prediction_strategies.py:268-272 -- the LOVE covariance cache).  parity unpinned.
+
+    Q, T = lanczos_tridiag(A, max_iter, init); T = V diag(lam) V^T with negative eigenvalues masked as in
+    lanczos_tridiag_to_diag; R = Q V diag(lam^-1/2).
+    """
+    q, t = lanczos_tridiag(matmul_closure, max_iter, init_vec.reshape(-1, 1), tol)
+    evals, evecs = tridiag_to_diag(t)
+    return q[0] @ (evecs[0] / evals[0].sqrt())
+
+
+def love_predictive_covar(k_ss, k_sx, inv_root):
+    """K** - (K*x R)(K*x R)^T  (exact_prediction_strategies.py:464-478)."""
+    root = k_sx @ inv_root
+    return k_ss - root @ root.transpose(-1, -2)

@@ -178,6 +178,22 @@ def test_pivoted_cholesky_stops_on_tolerance(Plan, cuda_dev):
     p.close()
 
 
+def test_pivoted_cholesky_persistent_and_stepwise_paths_agree(Plan, cuda_dev, monkeypatch):
+    """The cooperative single-launch kernel and the one-launch-per-step fallback run the same arithmetic per entry:
+    identical pivots and bit-identical factors (also with more rows than resident threads: grid-stride path)."""
+    for n, d, kind, rank in ((5000, 6, "rbf", 60), (3001, 3, "matern32", 25)):
+        x, _ = om.synthetic_problem(n, d, 0, torch.float32)
+        p = Plan(x.to(cuda_dev)).set_hypers(kind, 0.8, 1.3, 0.1)
+        monkeypatch.delenv("GP_PC_STEPWISE", raising=False)
+        lt1, piv1, _ = p.pivoted_cholesky(rank, 1e-4)
+        monkeypatch.setenv("GP_PC_STEPWISE", "1")
+        lt2, piv2, _ = p.pivoted_cholesky(rank, 1e-4)
+        monkeypatch.delenv("GP_PC_STEPWISE", raising=False)
+        assert piv1.cpu().tolist() == piv2.cpu().tolist()
+        assert torch.equal(lt1, lt2)
+        p.close()
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_mbcg_preconditioned_matches_oracle(Plan, cuda_dev, backend):
     n, d = 3000, 10
@@ -555,3 +571,51 @@ def test_api_function_seam_linear_cg_signature(cuda_dev):
     assert tmat.shape[0] == 2 and tmat.shape[-1] == tmat.shape[-2] <= 10
     L = gp.pivoted_cholesky(op, 20)
     assert L.shape == (n, 20)
+
+
+def test_api_love_fast_pred_var_matches_oracle_and_exact(cuda_dev):
+    """LOVE predictive covariance (settings.fast_pred_var; exact_prediction_strategies.py:268-272,
+    464-478) on the engine's Lanczos + fused cross-covariance K.V, against the oracle's restatement with the same
+    start vector (fp64) and against the exact predictive covariance."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+    from oracle import linalg as ol
+
+    n, m, d = 2600, 40, 3
+    x, y = om.synthetic_problem(n, d, 0, torch.float32)
+    g = torch.Generator().manual_seed(5)
+    xs = torch.rand(m, d, generator=g)
+    model, lik = _make_model(gp, x.to(cuda_dev), y.to(cuda_dev))
+    model.covar_module.base_kernel.lengthscale = 0.6
+    model.covar_module.outputscale = 1.3
+    lik.noise = 0.15
+    model.eval(); lik.eval()
+    with torch.no_grad(), settings.probe_seed(7), settings.max_root_decomposition_size(60), settings.eval_cg_tolerance(1e-4):
+        with settings.fast_pred_var(True):
+            love = model(xs.to(cuda_dev)).covariance_matrix.cpu().double()
+        exact = model(xs.to(cuda_dev)).covariance_matrix.cpu().double()
+        with settings.skip_posterior_variances(True):
+            assert float(model(xs.to(cuda_dev)).covariance_matrix.abs().max()) == 0.0
+    # oracle, fp64, same start vector
+    xd, xsd = x.double(), xs.double()
+    K = ok.kernel_matrix("rbf", xd, xd, 0.6, 1.3, True) + 0.15 * torch.eye(n, dtype=torch.float64)
+    ksx = ok.kernel_matrix("rbf", xsd, xd, 0.6, 1.3, False)
+    kss = ok.kernel_matrix("rbf", xsd, xsd, 0.6, 1.3, True)
+    init = torch.randn(n, generator=torch.Generator().manual_seed(7)).double()
+    r = ol.root_inv_decomposition(lambda v: K @ v, 60, init)
+    o_love = ol.love_predictive_covar(kss, ksx, r)
+    K32 = K.float()
+    r32 = ol.root_inv_decomposition(lambda v: K32 @ v, 60, init.float())          # the reference's own default dtype
+    o_love32 = ol.love_predictive_covar(kss.float(), ksx.float(), r32).double()
+    o_exact = kss - ksx @ torch.linalg.solve(K, ksx.T)
+    scale = o_exact.diagonal().mean().item()
+    # the truncated Krylov inverse amplifies fp32 rounding by cond(K_hat) ~ 1e4: stated tolerance = 2e-3 of the mean
+    # predictive variance, or no further from the fp64 oracle than 3x the fp32 run of the same algorithm
+    dev32 = (o_love32 - o_love).abs().max().item()
+    assert (love - o_love).abs().max().item() <= max(2e-3 * scale, 3 * dev32), ((love - o_love).abs().max().item(), dev32, scale)
+    # K** - K*x K_hat^-1 Kx* cancels from ~1.3 to ~2e-3: the CG solve (eval_cg_tolerance 1e-4, fp32) leaves an absolute
+    # error of ~tol * outputscale in every entry (the reference's default eval tolerance is 1e-2)
+    assert (exact - o_exact).abs().max().item() < 1e-3 * 1.3
+    # LOVE itself is an approximation of the exact covariance (60 Lanczos steps): loose, like the reference's own test
+    # (test/examples/test_simple_gp_regression.py: fast_pred_var variances within ~1e-2..5e-2)
+    assert (love.diagonal() - exact.diagonal()).abs().max().item() < 5e-2 * scale + 1e-3

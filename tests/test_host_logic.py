@@ -140,3 +140,25 @@ def test_shard_rows_cover_exactly():
             tot += c
         assert tot == n
         assert padded_size(n, w) % w == 0 and padded_size(n, w) >= n
+
+
+def test_oracle_love_root_reproduces_inverse_on_small_system():
+    """oracle.linalg.root_inv_decomposition: with J = N Lanczos steps R R^T is the exact inverse, so the LOVE covariance
+    equals the exact predictive covariance (exact_prediction_strategies.py:268-272, 464-478)."""
+    import torch
+    from oracle import kernels as ok, linalg as ol
+
+    torch.manual_seed(0)
+    n, m = 60, 7
+    x, xs = torch.rand(n, 2, dtype=torch.float64), torch.rand(m, 2, dtype=torch.float64)
+    K = ok.kernel_matrix("rbf", x, x, 0.5, 1.0, True) + 0.3 * torch.eye(n, dtype=torch.float64)
+    ksx = ok.kernel_matrix("rbf", xs, x, 0.5, 1.0, False)
+    kss = ok.kernel_matrix("rbf", xs, xs, 0.5, 1.0, True)
+    r = ol.root_inv_decomposition(lambda v: K @ v, n, torch.randn(n, dtype=torch.float64))
+    exact = kss - ksx @ torch.linalg.solve(K, ksx.T)
+    love = ol.love_predictive_covar(kss, ksx, r)
+    assert (love - exact).abs().max().item() < 1e-6
+    # and a truncated decomposition is a PSD under-estimate of the correction: predictive variances only grow
+    r20 = ol.root_inv_decomposition(lambda v: K @ v, 20, torch.randn(n, dtype=torch.float64))
+    love20 = ol.love_predictive_covar(kss, ksx, r20)
+    assert torch.all(love20.diagonal() >= exact.diagonal() - 1e-9)
