@@ -167,41 +167,45 @@ __device__ __forceinline__ void pc_grid_barrier(unsigned int* bar, unsigned int 
   __syncthreads();
 }
 
+constexpr int PCP_THREADS = 384;  // persistent kernel: one CTA per SM keeps the grid barrier small (148 arrivals)
+constexpr int PCP_RED = 512;
+
 template <int KIND>
-__global__ void __launch_bounds__(PC_THREADS)
+__global__ void __launch_bounds__(PCP_THREADS)
 pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, int64_t n, int max_rank, float tol,
                      float* diag, int* perm, int* pos, PcState* st, int64_t* piv_out, float* pval, int* ppos, double* psum) {
   extern __shared__ float sh[];
   float* zp = sh;           // [DP]
   float* lp = sh + DP;      // [max_rank]   L[q][pivot]
-  float* col = lp + max_rank;  // [max_rank][PC_THREADS]: L[q][j] of this thread's FIRST row (the dot product below is
+  float* col = lp + max_rank;  // [max_rank][PCP_THREADS]: L[q][j] of this thread's FIRST row (the dot product below is
                                // latency bound on L2 when it re-reads the column from Lt: 1.4 ms -> per 100 steps)
-  __shared__ float s_val[PC_THREADS];
-  __shared__ int s_pos[PC_THREADS];
-  __shared__ double s_sum[PC_THREADS];
+  __shared__ float s_val[PCP_RED];   // reduction trees run over PCP_RED = 512 slots; slots >= PCP_THREADS stay neutral
+  __shared__ int s_pos[PCP_RED];
+  __shared__ double s_sum[PCP_RED];
   const int tid = threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * PC_THREADS;
-  const int64_t jfirst = (int64_t)blockIdx.x * PC_THREADS + tid;
+  if (tid < PCP_RED - PCP_THREADS) { s_val[PCP_THREADS + tid] = -INFINITY; s_pos[PCP_THREADS + tid] = 0x7fffffff; s_sum[PCP_THREADS + tid] = 0.0; }
+  const int64_t stride = (int64_t)gridDim.x * PCP_THREADS;
+  const int64_t jfirst = (int64_t)blockIdx.x * PCP_THREADS + tid;
   unsigned int nbar = 0;
   for (int m = 0; m < max_rank; ++m) {
     const int pi = *((volatile int*)&st->pivot);
     const float dpiv = *((volatile float*)&st->dpiv);
-    for (int c = tid; c < DP; c += PC_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
-    for (int q = tid; q < m; q += PC_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM
+    for (int c = tid; c < DP; c += PCP_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+    for (int q = tid; q < m; q += PCP_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM
     __syncthreads();
     float best = -INFINITY;
     int best_pos = 0x7fffffff;
     double asum = 0.0;
     float* Lm = Lt + (int64_t)m * n;
-    for (int64_t j = (int64_t)blockIdx.x * PC_THREADS + tid; j < n; j += stride) {
+    for (int64_t j = (int64_t)blockIdx.x * PCP_THREADS + tid; j < n; j += stride) {
       const int pj = __ldcg(pos + j);
       const bool cached = (j == jfirst);
       if (pj < m) {
         Lm[j] = 0.f;
-        if (cached) col[m * PC_THREADS + tid] = 0.f;
+        if (cached) col[m * PCP_THREADS + tid] = 0.f;
       } else if (pj == m) {
         Lm[j] = dpiv;
-        if (cached) col[m * PC_THREADS + tid] = dpiv;
+        if (cached) col[m * PCP_THREADS + tid] = dpiv;
       } else {
         float s = 0.f;
         for (int c = 0; c < DP; ++c) {
@@ -215,12 +219,12 @@ pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, i
           if (cached) {   // same values, same order as the global-memory branch: bit-identical
             const float* cj = col + tid;
             for (; q + 4 <= m; q += 4) {
-              s0 = fmaf(lp[q], cj[q * PC_THREADS], s0);
-              s1 = fmaf(lp[q + 1], cj[(q + 1) * PC_THREADS], s1);
-              s2 = fmaf(lp[q + 2], cj[(q + 2) * PC_THREADS], s2);
-              s3 = fmaf(lp[q + 3], cj[(q + 3) * PC_THREADS], s3);
+              s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
+              s1 = fmaf(lp[q + 1], cj[(q + 1) * PCP_THREADS], s1);
+              s2 = fmaf(lp[q + 2], cj[(q + 2) * PCP_THREADS], s2);
+              s3 = fmaf(lp[q + 3], cj[(q + 3) * PCP_THREADS], s3);
             }
-            for (; q < m; ++q) s0 = fmaf(lp[q], cj[q * PC_THREADS], s0);
+            for (; q < m; ++q) s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
           } else {
             for (; q + 4 <= m; q += 4) {
               s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);          // column j is only ever written by this thread
@@ -234,7 +238,7 @@ pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, i
         }
         v /= dpiv;
         Lm[j] = v;
-        if (cached) col[m * PC_THREADS + tid] = v;
+        if (cached) col[m * PCP_THREADS + tid] = v;
         const float dn = diag[j] - v * v;
         diag[j] = dn;
         float cv; int cp;
@@ -246,8 +250,8 @@ pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, i
     }
     s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
     __syncthreads();
-    for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
-      if (tid < s) {
+    for (int s = PCP_RED / 2; s > 0; s >>= 1) {
+      if (tid < s && tid + s < PCP_RED) {
         float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
         if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
         s_sum[tid] += s_sum[tid + s];
@@ -258,14 +262,14 @@ pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, i
     pc_grid_barrier(&st->bar, (++nbar) * gridDim.x);   // (A) all partials are visible
     if (blockIdx.x == 0) {
       best = -INFINITY; best_pos = 0x7fffffff; asum = 0.0;
-      for (int b = tid; b < (int)gridDim.x; b += PC_THREADS) {   // fixed assignment + fixed tree => deterministic
+      for (int b = tid; b < (int)gridDim.x; b += PCP_THREADS) {   // fixed assignment + fixed tree => deterministic
         float v2 = __ldcg(pval + b); int p2 = __ldcg(ppos + b);
         if (v2 > best || (v2 == best && p2 < best_pos)) { best = v2; best_pos = p2; }
         asum += __ldcg(psum + b);
       }
       s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
       __syncthreads();
-      for (int s = PC_THREADS / 2; s > 0; s >>= 1) {
+      for (int s = PCP_RED / 2; s > 0; s >>= 1) {
         if (tid < s) {
           float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
           if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
@@ -464,7 +468,7 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device);
   if (coop && !stepwise) {
-    const size_t sh = sizeof(float) * (p->DP + rank + (size_t)rank * PC_THREADS);
+    const size_t sh = sizeof(float) * (p->DP + rank + (size_t)rank * PCP_THREADS);
     const void* fn;
     switch (p->kind) {
       case GP_RBF: fn = (const void*)pc_persistent_kernel<GP_RBF>; break;
@@ -474,14 +478,14 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
     }
     GP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     int per_sm = 0;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PC_THREADS, sh));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PCP_THREADS, sh));
     GP_REQUIRE(per_sm >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
-    const unsigned grid = std::min<unsigned>(gb, (unsigned)(per_sm * p->n_sm));   // gb partial slots are allocated
+    const unsigned grid = (unsigned)std::min<int64_t>(std::min<int64_t>(gb, cdiv(n, PCP_THREADS)), (int64_t)per_sm * p->n_sm);  // <= gb partial slots
     int DPv = p->DP, rk = rank;
     float osv = p->outputscale, tolv = error_tol;
     int64_t nn = n;
     void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &perm, &pos, &S, &piv, &pval, &ppos, &psum};
-    GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PC_THREADS), args, sh, st));
+    GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PCP_THREADS), args, sh, st));
     p->launches += 1;
   } else {
   for (int m = 0; m < rank; ++m) {
