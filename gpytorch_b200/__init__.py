@@ -2,7 +2,7 @@
 ExactMarginalLogLikelihood API surface.  The arithmetic lives in libgpbbmm.so (hand-written sm_100a CUDA,
 C ABI in include/gp_bbmm.h); this package is the thin Python host mirroring the reference interface.
 """
-from . import _lib, constraints, distributions, functions, kernels, likelihoods, means, mlls, models, settings  # noqa: F401
+from . import _lib, constraints, distributions, functions, kernels, likelihoods, means, mlls, models, operators, settings  # noqa: F401
 from ._lib import NanError, NumericalWarning  # noqa: F401
 from .engine import Plan  # noqa: F401
 from .functions import inv_quad_logdet, linear_cg, pivoted_cholesky, solve  # noqa: F401

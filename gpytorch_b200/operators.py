@@ -89,9 +89,9 @@ class KernelLinearOperator:
             self._plan = _get_plan(self.x1, None if self.same else self.x2, settings.backend.value(),
                                    self._row_begin, self._row_count, self._comm)
             fresh = True
-        key = (self.kind, tuple(_as_list(self.lengthscale)), float(self.outputscale), float(noise))
+        key = (self.kind, tuple(_as_list(self.lengthscale)), float(self.outputscale.detach()), float(noise))
         if fresh or getattr(self._plan, "_hyp_key", None) != key:
-            self._plan.set_hypers(self.kind, _as_list(self.lengthscale), float(self.outputscale), float(noise))
+            self._plan.set_hypers(self.kind, _as_list(self.lengthscale), float(self.outputscale.detach()), float(noise))
             self._plan._hyp_key = key
         return self._plan
 
@@ -125,6 +125,41 @@ class KernelLinearOperator:
     def representation(self):
         return (self.x1, self.x2, self.lengthscale, self.outputscale)
 
+    # -- LinearOperator protocol: shape helpers / transpose (lazy_evaluated_kernel_tensor.py:277-341) --
+    def _size(self):
+        return self.shape
+
+    @property
+    def matrix_shape(self):
+        return self.shape
+
+    def dim(self):
+        return 2
+
+    ndimension = dim
+
+    def numel(self):
+        return self.shape[0] * self.shape[1]
+
+    def _transpose_nonbatch(self):
+        """K(x1, x2)^T = K(x2, x1) for every stationary kernel on this path (no data is moved)."""
+        if self.same:
+            return self
+        return KernelLinearOperator(self.x2, self.x1, self.kind, self.lengthscale, self.outputscale)
+
+    def transpose(self, dim1, dim2):
+        return self if dim1 % 2 == dim2 % 2 else self._transpose_nonbatch()
+
+    def t(self):
+        return self._transpose_nonbatch()
+
+    @property
+    def mT(self):
+        return self._transpose_nonbatch()
+
+    def detach(self):
+        return KernelLinearOperator(self.x1, self.x2, self.kind, self.lengthscale.detach(), self.outputscale.detach())
+
     # -- products --
     def matmul(self, rhs):
         return _KernelMatmul.apply(self, rhs, self.lengthscale, self.outputscale)
@@ -141,6 +176,9 @@ class KernelLinearOperator:
         return self.plan().diag()
 
     _diagonal = diagonal
+
+    def _getitem(self, row_index, col_index, *batch_indices):
+        return self[row_index, col_index]
 
     def __getitem__(self, index):
         """Row / column slicing by re-indexing x1 / x2 (lazy_evaluated_kernel_tensor.py:136-243)."""
@@ -242,12 +280,64 @@ class AddedDiagLinearOperator:
         return self.kernel_op.matmul(rhs) + self.noise * rhs
 
     __matmul__ = matmul
+    _matmul = matmul
+
+    # -- LinearOperator protocol subset the callers use (SURVEY.md section 8b "Operator seam") --
+    def _size(self):
+        return self.shape
+
+    @property
+    def matrix_shape(self):
+        return self.shape
+
+    def dim(self):
+        return 2
+
+    ndimension = dim
+
+    def numel(self):
+        return self.shape[0] * self.shape[1]
+
+    @property
+    def requires_grad(self):
+        return bool(self.kernel_op.requires_grad or self.diag.diag_value.requires_grad)
+
+    def representation(self):
+        return self.kernel_op.representation() + (self.diag.diag_value,)
+
+    def transpose(self, dim1, dim2):
+        return self          # K + sigma^2 I is symmetric
+
+    def t(self):
+        return self
+
+    _transpose_nonbatch = t
+
+    @property
+    def mT(self):
+        return self
+
+    def detach(self):
+        return AddedDiagLinearOperator(self.kernel_op.detach(), ConstantDiagLinearOperator(self.diag.diag_value.detach(), self.shape[0]))
+
+    def __add__(self, other):
+        if isinstance(other, ConstantDiagLinearOperator):   # (K + a I) + b I
+            return AddedDiagLinearOperator(self.kernel_op, ConstantDiagLinearOperator(self.noise + other.diag_value.reshape(()), self.shape[0]))
+        raise NotImplementedError("AddedDiagLinearOperator only adds a ConstantDiagLinearOperator")
+
+    def logdet(self):
+        return self.inv_quad_logdet(None, logdet=True)[1]
+
+    def inv_quad(self, inv_quad_rhs, reduce_inv_quad=True):
+        return self.inv_quad_logdet(inv_quad_rhs, logdet=False, reduce_inv_quad=reduce_inv_quad)[0]
 
     def to_dense(self):
         return self.kernel_op.to_dense() + self.diag.to_dense()
 
     def diagonal(self, dim1=-2, dim2=-1):
         return self.kernel_op.diagonal() + self.noise
+
+    _diagonal = diagonal
 
     def add_jitter(self, jitter_val=1e-3):
         return AddedDiagLinearOperator(self.kernel_op, ConstantDiagLinearOperator(self.noise + jitter_val, self.shape[0]))

@@ -619,3 +619,67 @@ def test_api_love_fast_pred_var_matches_oracle_and_exact(cuda_dev):
     # LOVE itself is an approximation of the exact covariance (60 Lanczos steps): loose, like the reference's own test
     # (test/examples/test_simple_gp_regression.py: fast_pred_var variances within ~1e-2..5e-2)
     assert (love.diagonal() - exact.diagonal()).abs().max().item() < 5e-2 * scale + 1e-3
+
+
+def test_api_operator_seam_protocol_and_solve_vs_dense_inverse(cuda_dev):
+    """SURVEY 8(b) operator seam: the LinearOperator subset the reference's callers use, and the reference's own
+    solve-through-CG check (test/lazy/test_lazy_evaluated_kernel_tensor.py:69-113: vs evaluated.inverse(), rtol 0.02 /
+    atol 1e-5 under cg_tolerance(1e-4), gradients wrt the kernel parameters and the right-hand side)."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    n, m, d = 1100, 300, 3
+    x, _ = om.synthetic_problem(n, d, 0, torch.float32)
+    x2 = torch.rand(m, d, generator=torch.Generator().manual_seed(9))
+    kern = gp.kernels.ScaleKernel(gp.kernels.RBFKernel()).to(cuda_dev)
+    kern.base_kernel.lengthscale = 0.6
+    kern.outputscale = 1.2
+    op = kern(x.to(cuda_dev))
+    cross = kern(x.to(cuda_dev), x2.to(cuda_dev))
+    Kd = ok.kernel_matrix("rbf", x.double(), x.double(), 0.6, 1.2, True)
+    Kx = ok.kernel_matrix("rbf", x.double(), x2.double(), 0.6, 1.2, False)
+    # shape protocol
+    assert op.shape == op._size() == op.matrix_shape == torch.Size([n, n]) and op.dim() == 2 and op.numel() == n * n
+    assert cross.shape == torch.Size([n, m]) and cross.t().shape == cross.mT.shape == cross.transpose(-1, -2).shape == torch.Size([m, n])
+    assert op.batch_shape == torch.Size([]) and op.dtype == torch.float32 and op.device.type == "cuda" and op.requires_grad
+    assert len(op.representation()) == 4 and op.evaluate_kernel() is op and op.t() is op
+    # products: matmul / @ / transpose / diagonal / getitem / to_dense
+    v = torch.randn(m, 3, generator=torch.Generator().manual_seed(1))
+    w = torch.randn(n, 2, generator=torch.Generator().manual_seed(2))
+    assert rel((cross @ v.to(cuda_dev)).detach(), Kx @ v.double()) < 5e-6
+    assert rel(cross.t().matmul(w.to(cuda_dev)).detach(), Kx.T @ w.double()) < 5e-6
+    assert rel(op.diagonal().detach(), Kd.diagonal()) < 1e-6 and rel(op._diagonal().detach(), Kd.diagonal()) < 1e-6
+    assert rel(op[5:40, 100:260].to_dense().detach(), Kd[5:40, 100:260]) < 5e-6
+    assert rel(op._getitem(slice(0, 16), slice(None)).to_dense().detach(), Kd[:16]) < 5e-6
+    khat = op + gp.operators.ConstantDiagLinearOperator(torch.tensor(0.3, device=cuda_dev), n)
+    khat2 = khat.add_jitter(0.2)
+    assert float(khat2.noise) == pytest.approx(0.5) and khat.t() is khat and khat.shape == op.shape and khat.requires_grad
+    assert rel(khat2.diagonal().detach(), Kd.diagonal() + 0.5) < 1e-6
+    assert rel((khat @ w.to(cuda_dev)).detach(), (Kd + 0.3 * torch.eye(n, dtype=torch.float64)) @ w.double()) < 5e-6
+    # solve through CG vs the dense inverse, with gradients (the reference's _test_inv_matmul)
+    rhs = torch.randn(n, 4, generator=torch.Generator().manual_seed(3)).to(cuda_dev).requires_grad_(True)
+    with settings.max_cholesky_size(0), settings.cg_tolerance(1e-4), settings.max_preconditioner_size(30):
+        res = khat.solve(rhs)
+        grad = torch.randn(n, 4, generator=torch.Generator().manual_seed(4))
+        res.backward(gradient=grad.to(cuda_dev))
+    ls = torch.tensor(0.6, dtype=torch.float64, requires_grad=True)
+    osc = torch.tensor(1.2, dtype=torch.float64, requires_grad=True)
+    rhs_c = rhs.detach().cpu().double().requires_grad_(True)
+    Ka = ok.kernel_matrix("rbf", x.double(), x.double(), ls, osc, True) + 0.3 * torch.eye(n, dtype=torch.float64)
+    actual = torch.linalg.solve(Ka, rhs_c)
+    actual.backward(gradient=grad.double())
+    # the reference's own bound is rtol 0.02 / atol 1e-5 on a 5 x 5 system; at n = 1100 with cg_tolerance(1e-4) the fp32
+    # solve carries ~1e-4 of the solution norm in every entry, so the absolute part is scaled accordingly
+    assert rel(res.detach(), actual.detach()) < 1e-3
+    assert torch.allclose(res.detach().cpu().double(), actual.detach(), rtol=0.02, atol=2e-3)
+    g_ls = kern.base_kernel.raw_lengthscale.grad.item() / torch.sigmoid(kern.base_kernel.raw_lengthscale).item()
+    g_os = kern.raw_outputscale.grad.item() / torch.sigmoid(kern.raw_outputscale).item()
+    assert g_ls == pytest.approx(ls.grad.item(), rel=1e-2, abs=1e-3)
+    assert g_os == pytest.approx(osc.grad.item(), rel=1e-2, abs=1e-3)
+    assert rel(rhs.grad, rhs_c.grad) < 1e-3 and torch.allclose(rhs.grad.cpu().double(), rhs_c.grad, rtol=0.03, atol=2e-3)
+    # log-det / inv-quad shortcuts
+    with settings.max_cholesky_size(0), settings.probe_seed(0), settings.num_trace_samples(15), settings.max_preconditioner_size(30):
+        ld = khat.logdet().item()
+        iq = khat.inv_quad(rhs.detach()[:, :1]).item()
+    assert ld == pytest.approx(torch.logdet(Ka.detach()).item(), rel=5e-2)
+    assert iq == pytest.approx((rhs_c.detach()[:, :1] * torch.linalg.solve(Ka.detach(), rhs_c.detach()[:, :1])).sum().item(), rel=1e-3)
