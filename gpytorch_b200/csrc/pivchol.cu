@@ -323,8 +323,8 @@ __global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm,
 // ---- preconditioner factor ---------------------------------------------------------------------
 // Gpart[z][a][b] = sum_{j in slice z} L[a][j] L[b][j]   (fp64)
 __global__ void gram_kernel(const float* __restrict__ Lt, int k, int64_t n, int64_t jslice, double* __restrict__ Gpart) {
-  __shared__ float A[16][65];
-  __shared__ float B[16][65];
+  __shared__ double A[16][65];   // staged as fp64: the (exact) conversion happens once per element, not once per FMA
+  __shared__ double B[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
   const int64_t j_begin = (int64_t)blockIdx.z * jslice, j_end = min(n, j_begin + jslice);
@@ -334,12 +334,12 @@ __global__ void gram_kernel(const float* __restrict__ Lt, int k, int64_t n, int6
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
       int r = e >> 6, cc = e & 63;
       int64_t j = j0 + cc;
-      A[r][cc] = (a0 + r < k && j < j_end) ? Lt[(int64_t)(a0 + r) * n + j] : 0.f;
-      B[r][cc] = (b0 + r < k && j < j_end) ? Lt[(int64_t)(b0 + r) * n + j] : 0.f;
+      A[r][cc] = (a0 + r < k && j < j_end) ? (double)Lt[(int64_t)(a0 + r) * n + j] : 0.0;
+      B[r][cc] = (b0 + r < k && j < j_end) ? (double)Lt[(int64_t)(b0 + r) * n + j] : 0.0;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int cc = 0; cc < 64; ++cc) acc = fma((double)A[ty][cc], (double)B[tx][cc], acc);
+    for (int cc = 0; cc < 64; ++cc) acc = fma(A[ty][cc], B[tx][cc], acc);
   }
   if (a0 + ty < k && b0 + tx < k) Gpart[((int64_t)blockIdx.z * k + a0 + ty) * k + b0 + tx] = acc;
 }
@@ -367,10 +367,10 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
     for (int i = j + 1 + tid; i < k; i += blockDim.x) G[i * k + j] /= djj;
     __syncthreads();
     // trailing update: G[i][l] -= G[i][j] G[l][j] for j < l <= i
-    const int rem = k - j - 1;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      int i = j + 1 + e / rem, l = j + 1 + e % rem;
-      if (l <= i) G[i * k + l] -= G[i * k + j] * G[l * k + j];
+    // (2-D thread mapping, no integer division: every (i, l) is still updated exactly once with the same operands)
+    for (int i = j + 1 + (tid >> 5); i < k; i += (int)(blockDim.x >> 5)) {
+      const double gij = G[i * k + j];
+      for (int l = j + 1 + (tid & 31); l <= i; l += 32) G[i * k + l] -= gij * G[l * k + j];
     }
     __syncthreads();
   }
@@ -384,38 +384,44 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
 
 // Cinv = C^{-1} (lower triangular, fp64): one thread per column, forward substitution against C in shared memory
 __global__ void cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
-  extern __shared__ double Cs[];  // [k][k]
-  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cs[e] = C[e];
-  __syncthreads();
+  extern __shared__ double Is[];  // [k][k] C^{-1}, built column by column in shared memory (C itself: broadcast loads, L1)
   const int j = threadIdx.x;
-  if (j >= k) return;
-  for (int i = 0; i < k; ++i) {
-    double s = (i == j) ? 1.0 : 0.0;
-    for (int b = j; b < i; ++b) s -= Cs[i * k + b] * Cinv[(size_t)b * k + j];
-    Cinv[(size_t)i * k + j] = (i < j) ? 0.0 : s / Cs[i * k + i];
+  if (j < k) {
+    for (int i = 0; i < k; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int b = j; b < i; ++b) s -= __ldg(C + i * k + b) * Is[b * k + j];
+      Is[i * k + j] = (i < j) ? 0.0 : s / __ldg(C + i * k + i);
+    }
   }
+  __syncthreads();
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cinv[e] = Is[e];
 }
 
-// W[r][a] = sum_{b<=a} Cinv[a][b] L[b][r]   (W = L C^{-T}); 32 rows x 4 interleaved a-groups per CTA, fp64 accumulate
+constexpr int WS_BLOCKS = 4;
+// W[r][a] = sum_{b<=a} Cinv[a][b] L[b][r]   (W = L C^{-T}); 32 rows x 4 interleaved a-groups per pass, fp64 accumulate
 __global__ void __launch_bounds__(128)
 wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
               const double* __restrict__ Cinv, float* __restrict__ W) {
   extern __shared__ double shw[];
-  double* Ci = shw;                                            // [k][k]
-  float* Ls = reinterpret_cast<float*>(shw + (size_t)k * k);   // [k][32]
+  double* Ci = shw;                        // [k][k]
+  double* Ls = shw + (size_t)k * k;        // [k][32], fp64 copy of the L rows (exact conversion, once per element)
   for (int e = threadIdx.x; e < k * k; e += 128) Ci[e] = Cinv[e];
   const int rl = threadIdx.x & 31, ag = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  for (int e = threadIdx.x; e < k * 32; e += 128) {
-    int b = e >> 5, rr = e & 31;
-    Ls[e] = (r0 + rr < n_local) ? Lt[(int64_t)b * n_total + row_begin + r0 + rr] : 0.f;
-  }
-  __syncthreads();
-  const int64_t r = r0 + rl;
-  for (int a = ag; a < k; a += 4) {
-    double s = 0.0;
-    for (int b = 0; b <= a; ++b) s = fma(Ci[a * k + b], (double)Ls[b * 32 + rl], s);
-    if (r < n_local) W[r * k + a] = (float)s;
+  for (int blk = 0; blk < WS_BLOCKS; ++blk) {          // C^{-1} (80 KB at k = 100) is loaded once per WS_BLOCKS * 32 rows
+    const int64_t r0 = ((int64_t)blockIdx.x * WS_BLOCKS + blk) * 32;
+    if (r0 >= n_local) break;
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * 32; e += 128) {
+      int b = e >> 5, rr = e & 31;
+      Ls[e] = (r0 + rr < n_local) ? (double)Lt[(int64_t)b * n_total + row_begin + r0 + rr] : 0.0;
+    }
+    __syncthreads();
+    const int64_t r = r0 + rl;
+    for (int a = ag; a < k; a += 4) {
+      double s = 0.0;
+      for (int b = 0; b <= a; ++b) s = fma(Ci[a * k + b], Ls[b * 32 + rl], s);
+      if (r < n_local) W[r * k + a] = (float)s;
+    }
   }
 }
 
@@ -531,12 +537,12 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
   dim3 gg((unsigned)cdiv(k, 16), (unsigned)cdiv(k, 16), (unsigned)nz);
   gram_kernel<<<gg, 256, 0, st>>>(Lt, k, n, jslice, p->gram.as<double>());
   size_t shc = sizeof(double) * (size_t)k * k;
-  GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // k <= 128: 128 KB
+  GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));         // 128 KB + 32 KB
   chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, (double)p->noise, n, C, d_logdet, d_fail);
   GP_CUDA(cudaFuncSetAttribute(cinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   cinv_kernel<<<1, 128, shc, st>>>(C, k, Cinv);
-  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32), 128, shc + sizeof(float) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin, p->row_count, Cinv, W);
+  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32 * WS_BLOCKS), 128, shc + sizeof(double) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin, p->row_count, Cinv, W);
   p->launches += 4;
   GP_CUDA(cudaGetLastError());
   double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(p->pinned) + 3072);
