@@ -361,10 +361,11 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   int ns = 0;
   int smem_bytes = tc_smem_bytes(p->KP, &ns);
   GP_REQUIRE(ns >= 3, GP_E_SHAPE, "tcgen05 path: smem ring too small for KP=%d", p->KP);
-  static bool attr_done[2 * GP_DERIV] = {};
-  if (!attr_done[KIND]) {
+  static bool attr_done[64] = {};   // function attributes are per device
+  const int dev_slot = p->device & 63;
+  if (!attr_done[dev_slot]) {
     GP_CUDA(cudaFuncSetAttribute(kmv_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[KIND] = true;
+    attr_done[dev_slot] = true;
   }
   int64_t rows_pad = p->ntile_i * TILE_I;
   dim3 grid((unsigned)p->ntile_i, (unsigned)p->nsplit);
