@@ -25,5 +25,8 @@ Pinning status
   anchored instead on dense-Cholesky ground truth (solve / log-det / MLL) and
   on the reference's call sites (``distributions/multivariate_normal.py:248-251``,
   ``variational/ciq_variational_strategy.py:56-64``).
+* ``oracle/ski.py`` (SKI / KISS-GP, groundwork for SURVEY.md section 8f row 3): the interpolation and grid helpers are
+  PINNED against outputs of the reference's own code (``tests/golden/ski_golden.npz``); the Toeplitz / Kronecker
+  products restate linear_operator and are **parity unpinned** (checked against dense matrices).
 """
-from . import kernels, linalg, mll  # noqa: F401
+from . import kernels, linalg, mll, ski  # noqa: F401
