@@ -228,25 +228,42 @@ def pivoted_cholesky(diag, get_row, rank, error_tol=PRECONDITIONER_TOLERANCE):
 @dataclass
 class Preconditioner:
     L: torch.Tensor  # [N, k] pivoted Cholesky factor
-    Q: torch.Tensor  # [N, k] top block of qr([L; sigma I])
-    noise: float
+    Q: torch.Tensor  # [N, k] top block of qr([L; sigma I])   (per-row noise: of qr([D^-1/2 L; I]), rows scaled by D^-1/2)
+    noise: object    # float (constant diagonal) or tensor [N] (per-row noise, FixedNoiseGaussianLikelihood)
     logdet: float
     pivots: torch.Tensor | None = None
 
+    def _d(self, like):
+        d = self.noise
+        return d.to(like).reshape(-1, 1) if torch.is_tensor(d) else d
+
     def apply(self, v):
-        """P^{-1} v = (v - Q Q^T v) / sigma^2 (AddedDiagLinearOperator._preconditioner closure)."""
+        """P^{-1} v = (v - Q Q^T v) / sigma^2 (AddedDiagLinearOperator._preconditioner closure); with a per-row diagonal
+        P^{-1} v = v / d - Q~ Q~^T v, Q~ = D^-1/2 Q  (the non-constant-diagonal closure)."""
+        if torch.is_tensor(self.noise):
+            return v / self._d(v) - self.Q @ (self.Q.t() @ v)
         return (v - self.Q @ (self.Q.t() @ v)) / self.noise
 
     def probes(self, eps1, eps2):
-        """z ~ N(0, P), P = L L^T + sigma^2 I, as z = L eps1 + sigma eps2."""
+        """z ~ N(0, P), P = L L^T + D, as z = L eps1 + D^1/2 eps2."""
+        if torch.is_tensor(self.noise):
+            return self.L @ eps1 + self._d(eps2).sqrt() * eps2
         return self.L @ eps1 + math.sqrt(self.noise) * eps2
 
 
 def build_preconditioner(L, noise, pivots=None):
     """QR of [L; sigma I], log det P = 2 sum log|R_ii| + (N-k) log sigma^2
-    (AddedDiagLinearOperator._init_cache_for_constant_diag)."""
+    (AddedDiagLinearOperator._init_cache_for_constant_diag).  A tensor `noise` [N] takes the non-constant-diagonal branch
+    (_init_cache_for_non_constant_diag): QR of [D^-1/2 L; I], Q~ = D^-1/2 Q[:N], log det P = 2 sum log|R_ii| + sum log d_i."""
     n, k = L.shape
     eye = torch.eye(k, dtype=L.dtype)
+    if torch.is_tensor(noise) and noise.numel() > 1:
+        d = noise.to(L.dtype).reshape(-1, 1)
+        Q, R = torch.linalg.qr(torch.cat((L / d.sqrt(), eye), dim=-2))
+        Q = Q[:n] / d.sqrt()
+        logdet = float(R.diagonal().abs().log().sum() * 2 + d.log().sum())
+        return Preconditioner(L=L, Q=Q, noise=noise.to(L.dtype).reshape(-1), logdet=logdet, pivots=pivots)
+    noise = float(noise)
     Q, R = torch.linalg.qr(torch.cat((L, math.sqrt(noise) * eye), dim=-2))
     Q = Q[:n]
     logdet = float(R.diagonal().abs().log().sum() * 2 + (n - k) * math.log(noise))

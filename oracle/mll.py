@@ -39,11 +39,17 @@ def make_probe_noise(n, k, tp, seed, dtype=torch.float32):
     return eps1, eps2, rad
 
 
+def _noise_diag(noise, n, dtype):
+    if torch.is_tensor(noise) and noise.numel() > 1:
+        return torch.diag(noise.to(dtype).reshape(-1))
+    return float(noise) * torch.eye(n, dtype=dtype)
+
+
 def mll_cholesky(kind, x, y, mean, lengthscale, outputscale, noise):
     """Dense ground truth (the reference's own N <= max_cholesky_size branch)."""
     n = x.size(-2)
     K = kernels.kernel_matrix(kind, x, x, lengthscale, outputscale, True)
-    Khat = K + noise * torch.eye(n, dtype=x.dtype)
+    Khat = K + _noise_diag(noise, n, x.dtype)   # scalar sigma^2, or a per-row vector (FixedNoiseGaussianLikelihood)
     Lc = torch.linalg.cholesky(Khat)
     r = (y - mean).unsqueeze(-1)
     sol = torch.cholesky_solve(r, Lc)
@@ -78,8 +84,13 @@ def mll_bbmm(
     if K is None:
         K = kernels.kernel_matrix(kind, x, x, lengthscale, outputscale, True)
 
+    per_row = torch.is_tensor(noise) and noise.numel() > 1
+    nz = noise.to(x.dtype).reshape(-1) if per_row else noise
+
     def matmul(v):
-        return K @ v + noise * v
+        if per_row:
+            return K @ v + (nz.unsqueeze(-1) * v if v.dim() > 1 else nz * v)
+        return K @ v + nz * v
 
     eps1, eps2, rad = probe_noise
     precond = None

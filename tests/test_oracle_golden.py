@@ -180,3 +180,36 @@ def test_lanczos_orthogonal_basis(problem):
     Q, T = Q[0], T[0]
     assert (Q.t() @ Q - torch.eye(T.size(0), dtype=torch.float64)).abs().max() < 1e-10
     assert (Q.t() @ A @ Q - T).abs().max() < 1e-8
+
+
+def test_per_row_noise_preconditioner_and_mll_against_dense():
+    """Groundwork for FixedNoiseGaussianLikelihood (likelihoods/gaussian_likelihood.py:245-363): the
+    non-constant-diagonal preconditioner branch and the BBMM MLL with a per-row noise vector vs dense linear algebra."""
+    torch.manual_seed(3)
+    n, k = 400, 12
+    x, y = om.synthetic_problem(n, 3, 0, torch.float64)
+    K = ok.kernel_matrix("rbf", x, x, 0.6, 1.0, True)
+    d = 0.05 + 0.3 * torch.rand(n, dtype=torch.float64)
+    L, piv = ol.pivoted_cholesky(torch.ones(n, dtype=torch.float64), lambda i: K[i], k, 1e-6)
+    pre = ol.build_preconditioner(L, d, piv)
+    P = L @ L.t() + torch.diag(d)
+    v = torch.randn(n, 3, dtype=torch.float64)
+    assert (pre.apply(v) - torch.linalg.solve(P, v)).abs().max().item() < 1e-9
+    assert pre.logdet == pytest.approx(torch.logdet(P).item(), rel=1e-10)
+    e1, e2 = torch.randn(L.size(1), 20000, dtype=torch.float64), torch.randn(n, 20000, dtype=torch.float64)
+    z = pre.probes(e1, e2)
+    emp = (z[:5] @ z[:5].t()) / 20000
+    assert (emp - P[:5, :5]).abs().max().item() < 0.06           # z ~ N(0, P)
+    # constant vector == scalar branch
+    pre_c = ol.build_preconditioner(L, torch.full((n,), 0.2, dtype=torch.float64), piv)
+    pre_s = ol.build_preconditioner(L, 0.2, piv)
+    assert (pre_c.apply(v) - pre_s.apply(v)).abs().max().item() < 1e-10 and pre_c.logdet == pytest.approx(pre_s.logdet, rel=1e-12)
+    # MLL with per-row noise: mBCG/SLQ vs dense Cholesky
+    n2 = 2100
+    x2, y2 = om.synthetic_problem(n2, 3, 0, torch.float64)
+    d2 = 0.05 + 0.2 * torch.rand(n2, dtype=torch.float64)
+    pn = tuple(a.double() for a in om.make_probe_noise(n2, 30, 10, 1))
+    ch = om.mll_cholesky("rbf", x2, y2, 0.0, 0.7, 1.0, d2)
+    bb = om.mll_bbmm("rbf", x2, y2, 0.0, 0.7, 1.0, d2, pn, precond_size=30, tolerance=1e-3)
+    assert bb.inv_quad == pytest.approx(ch.inv_quad, rel=1e-3)
+    assert bb.logdet == pytest.approx(ch.logdet, rel=3e-2)
