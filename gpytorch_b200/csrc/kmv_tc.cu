@@ -4,7 +4,7 @@
 //   sq_dist GEMM + exp over N^2          kernels/kernel.py:26-49, functions/rbf_covariance.py:14-19
 //   Matern poly*exp passes               functions/matern_covariance.py:21-47
 //   dense K @ V inside linear_cg         lazy/lazy_evaluated_kernel_tensor.py:245-276 (chunked form)
-// The N x N matrix K never exists in HBM: per 128 x 96 tile it lives in TMEM only.
+// The N x N matrix K never exists in HBM: per 128 x 64 tile it lives in TMEM only.
 //
 // One CTA (320 threads; TWO CTAs are resident per SM) owns one work unit = (128-row tile of K) x (a contiguous range of
 // 64-column tiles).  Per column tile u (TMEM slot u % 2, epilogue warpgroup u % 2):
