@@ -162,3 +162,41 @@ def test_oracle_love_root_reproduces_inverse_on_small_system():
     r20 = ol.root_inv_decomposition(lambda v: K @ v, 20, torch.randn(n, dtype=torch.float64))
     love20 = ol.love_predictive_covar(kss, ksx, r20)
     assert torch.all(love20.diagonal() >= exact.diagonal() - 1e-9)
+
+
+def test_operator_protocol_without_compute():
+    """Shape / transpose / lazy-slicing protocol of the covariance operators needs no device work
+    (lazy_evaluated_kernel_tensor.py:136-243, 277-341): it must behave on CPU tensors, and only products may fail."""
+    import torch
+    import gpytorch_b200 as gp
+    from gpytorch_b200.operators import AddedDiagLinearOperator, ConstantDiagLinearOperator, KernelLinearOperator
+
+    x1, x2 = torch.rand(30, 4), torch.rand(12, 4)
+    ls = torch.tensor(0.5)
+    sq = KernelLinearOperator(x1, None, "rbf", ls)
+    cr = KernelLinearOperator(x1, x2, "matern52", ls, torch.tensor(2.0))
+    assert sq.shape == sq._size() == sq.matrix_shape == torch.Size([30, 30]) and sq.dim() == 2 and sq.numel() == 900
+    assert cr.shape == torch.Size([30, 12]) and cr.t().shape == cr.mT.shape == cr.transpose(-2, -1).shape == torch.Size([12, 30])
+    assert cr.transpose(-1, -1) is cr and sq.t() is sq and cr.t().t().shape == cr.shape
+    assert cr.t().x1 is x2 and cr.t().x2 is x1 and cr.t().kind == "matern52"
+    sub = sq[3:9, 10:20]
+    assert isinstance(sub, KernelLinearOperator) and sub.shape == torch.Size([6, 10]) and not sub.same
+    assert sq._getitem(slice(0, 5), slice(None)).shape == torch.Size([5, 30])
+    assert sq.batch_shape == torch.Size([]) and sq.dtype == torch.float32 and not sq.requires_grad
+    assert KernelLinearOperator(x1, None, "rbf", ls.clone().requires_grad_(True)).requires_grad
+    assert sq.detach().shape == sq.shape and len(sq.representation()) == 4 and sq.evaluate_kernel() is sq
+    khat = sq + ConstantDiagLinearOperator(torch.tensor(0.1), 30)
+    assert isinstance(khat, AddedDiagLinearOperator) and khat.shape == sq.shape and khat.t() is khat and khat.mT is khat
+    assert float(khat.add_jitter(0.2).noise) == pytest.approx(0.3)
+    assert float((khat + ConstantDiagLinearOperator(torch.tensor(0.4), 30)).noise) == pytest.approx(0.5)
+    assert len(khat.representation()) == 5 and not khat.requires_grad and khat.dim() == 2
+    with pytest.raises(RuntimeError, match="square"):
+        AddedDiagLinearOperator(cr, ConstantDiagLinearOperator(torch.tensor(0.1), 30))
+    with pytest.raises(NotImplementedError):
+        sq + sq
+    with pytest.raises(RuntimeError):      # products need the CUDA engine: no CPU fallback
+        sq.matmul(torch.rand(30, 2))
+    assert gp.settings.fast_pred_var.off() and gp.settings.skip_posterior_variances.off()
+    with gp.settings.fast_pred_var(True), gp.settings.skip_posterior_variances(True):
+        assert gp.settings.fast_pred_var.on() and gp.settings.skip_posterior_variances.on()
+    assert gp.settings.fast_pred_var.off()
