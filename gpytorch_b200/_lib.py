@@ -13,7 +13,7 @@ import warnings
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPBBMM_LIB") or os.path.join(_HERE, "lib", "libgpbbmm.so")   # GPBBMM_LIB: see INTEGRATION.md
 
-GP_OK, GP_E_SHAPE, GP_E_CUDA, GP_E_NAN_MVM, GP_W_NOT_CONVERGED, GP_W_PIVCHOL_NAN, GP_E_NCCL, GP_E_STATE = range(8)
+GP_OK, GP_E_SHAPE, GP_E_CUDA, GP_E_NAN_MVM, GP_W_NOT_CONVERGED, GP_W_PIVCHOL_NAN, GP_E_NCCL, GP_E_STATE, GP_W_EIG_NOT_CONVERGED = range(9)
 GP_RBF, GP_MATERN12, GP_MATERN32, GP_MATERN52 = range(4)
 GP_BACKEND_AUTO, GP_BACKEND_TCGEN05, GP_BACKEND_SIMT = range(3)
 KIND = {"rbf": GP_RBF, "matern12": GP_MATERN12, "matern32": GP_MATERN32, "matern52": GP_MATERN52}
@@ -122,7 +122,7 @@ def check(status: int, warn: bool = True) -> int:
         if warn:
             warnings.warn(msg, NumericalWarning)
         return status
-    if status == GP_W_PIVCHOL_NAN:
+    if status in (GP_W_PIVCHOL_NAN, GP_W_EIG_NOT_CONVERGED):
         if warn:
             warnings.warn(msg, NumericalWarning)
         return status

@@ -1,4 +1,5 @@
-"""Parameter constraints (mirror of gpytorch/constraints/constraints.py:156-194): softplus transforms."""
+"""Parameter constraints (mirror of gpytorch/constraints/constraints.py:17-194): softplus transforms; the bounds are
+registered buffers named `lower_bound` / `upper_bound` (:44-45) so that state dicts are interchangeable."""
 import math
 
 import torch
@@ -12,8 +13,20 @@ def inv_softplus(x):
 class Interval(torch.nn.Module):
     def __init__(self, lower_bound=-math.inf, upper_bound=math.inf):
         super().__init__()
-        self.lower_bound = float(lower_bound)
-        self.upper_bound = float(upper_bound)
+        dtype = torch.get_default_dtype()
+        lower_bound = torch.as_tensor(lower_bound).to(dtype)
+        upper_bound = torch.as_tensor(upper_bound).to(dtype)
+        if torch.any(torch.ge(lower_bound, upper_bound)):
+            raise ValueError("Got parameter bounds with empty intervals.")   # constraints.py:31-32
+        self.register_buffer("lower_bound", lower_bound)
+        self.register_buffer("upper_bound", upper_bound)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # constraints.py:62-77: the bound buffers may be absent from older state dicts -> never strict here
+        return super()._load_from_state_dict(state_dict, prefix, local_metadata, False, missing_keys, unexpected_keys, error_msgs)
+
+    def check(self, tensor) -> bool:
+        return bool(torch.all(tensor <= self.upper_bound) and torch.all(tensor >= self.lower_bound))
 
     def transform(self, raw):
         return raw

@@ -71,6 +71,7 @@ extern "C" const char* gp_status_string(int s) {
     case GP_W_PIVCHOL_NAN: return "NaNs encountered in preconditioner computation";
     case GP_E_NCCL: return "NCCL error";
     case GP_E_STATE: return "call order violated";
+    case GP_W_EIG_NOT_CONVERGED: return "tridiagonal eigen-solver did not converge";
   }
   return "unknown";
 }
@@ -308,7 +309,11 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   mark();
 
   double logdet = 0.0;
-  GP_CHECK(gp_slq_logdet(p, tmat, tp, o->max_tridiag_iter, J, N, &logdet));
+  {
+    int st_slq = gp_slq_logdet(p, tmat, tp, o->max_tridiag_iter, J, N, &logdet);
+    if (st_slq == GP_W_EIG_NOT_CONVERGED) flags |= 4;
+    else GP_CHECK(st_slq);
+  }
   invquad_kernel<<<64, 256, 0, st>>>(solves, t, tp, y_minus_mean, n, iq_part);
   p->launches++;
   if (solve_out) {

@@ -423,6 +423,15 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   cudaStream_t st = p->stream;
   const int64_t n = p->row_count;       // local rows
   const int64_t N = p->n2;              // global size
+  if (p->comm && p->comm->world > 1) {
+    // the all-gather of the direction blocks needs equal, rank-ordered shards (ncclAllGather has one count for all ranks)
+    GP_REQUIRE(n * p->comm->world == N && p->row_begin == (int64_t)p->comm->rank * n, GP_E_SHAPE,
+               "row-sharded mBCG needs equal contiguous shards: rank %d/%d owns [%lld,+%lld) of %lld rows (pad N to a multiple of the world size)",
+               p->comm->rank, p->comm->world, (long long)p->row_begin, (long long)n, (long long)N);
+  } else {
+    GP_REQUIRE(n == N && p->row_begin == 0, GP_E_SHAPE, "a row shard [%lld,+%lld) of %lld rows needs a communicator (gp_plan_set_comm)",
+               (long long)p->row_begin, (long long)n, (long long)N);
+  }
   const float eps = 1e-10f, stop_after = 1e-10f;
   const int n_tridiag_iter = (int)std::min<int64_t>(max_tridiag_iter, N);
   const bool precond = W != nullptr;

@@ -144,11 +144,16 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
 // ---- row extraction: OUT[m][n2] = os * k(x1[idx[r]], x2[j]) -----------------------------------
 template <int KIND>
 __global__ void krows_kernel(const float* __restrict__ Z1, const float* __restrict__ Z2, int DP,
-                             const int64_t* __restrict__ idx, int64_t n2, float os, int same, int64_t row_begin,
-                             float* __restrict__ OUT, int64_t ldo) {
+                             const int64_t* __restrict__ idx, int64_t n1_local, int64_t n2, float os, int same,
+                             int64_t row_begin, float* __restrict__ OUT, int64_t ldo) {
   extern __shared__ float zi[];
   const int64_t r = blockIdx.y;
   const int64_t i = idx[r];
+  if (i < 0 || i >= n1_local) {   // out-of-range row index (CTA-uniform): NaN row instead of an out-of-bounds read
+    int64_t jj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj < n2) OUT[r * ldo + jj] = __int_as_float(0x7fc00000);
+    return;
+  }
   for (int c = threadIdx.x; c < DP; c += blockDim.x) zi[c] = Z1[i * DP + c];
   __syncthreads();
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +166,21 @@ __global__ void krows_kernel(const float* __restrict__ Z1, const float* __restri
   float a = -0.5f * s;
   if (same && (i + row_begin) == j) a = 0.f;
   OUT[r * ldo + j] = os * cov_from_arg<KIND>(a);
+}
+
+// diagonal of a cross-covariance K(x1, x2) (n1 == n2): OUT[i] = os * k(x1_i, x2_i)   (kernel(x1, x2, diag=True),
+// lazy_evaluated_kernel_tensor.py:107-133 / kernels/kernel.py:307-352 with diag=True)
+template <int KIND>
+__global__ void kdiag_cross_kernel(const float* __restrict__ Z1, const float* __restrict__ Z2, int DP, int64_t n, float os,
+                                   float* __restrict__ OUT) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < DP; ++c) {
+    float df = Z1[i * DP + c] - Z2[i * DP + c];
+    s = fmaf(df, df, s);
+  }
+  OUT[i] = os * cov_from_arg<KIND>(-0.5f * s);
 }
 
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
@@ -310,10 +330,10 @@ extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, i
   dim3 grid((unsigned)cdiv(p->n2, 256), (unsigned)m);
   size_t sh = sizeof(float) * p->DP;
   switch (p->kind) {
-    case GP_RBF: krows_kernel<GP_RBF><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
-    case GP_MATERN12: krows_kernel<GP_MATERN12><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
-    case GP_MATERN32: krows_kernel<GP_MATERN32><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
-    default: krows_kernel<GP_MATERN52><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
+    case GP_RBF: krows_kernel<GP_RBF><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->row_count, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
+    case GP_MATERN12: krows_kernel<GP_MATERN12><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->row_count, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
+    case GP_MATERN32: krows_kernel<GP_MATERN32><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->row_count, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
+    default: krows_kernel<GP_MATERN52><<<grid, 256, sh, p->stream>>>(Z1, p->Z2.as<float>(), p->DP, idx, p->row_count, p->n2, p->outputscale, p->same, p->row_begin, OUT, ldo); break;
   }
   p->launches++;
   GP_CUDA(cudaGetLastError());
@@ -322,8 +342,22 @@ extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, i
 
 extern "C" int gp_kdiag(gp_plan* p, float* OUT) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
-  // stationary kernels: k(x,x) = outputscale (lazy_evaluated_kernel_tensor.py:107-133 evaluates kernel(diag=True))
-  fill_kernel<<<(unsigned)cdiv(p->row_count, 256), 256, 0, p->stream>>>(OUT, p->row_count, p->outputscale);
+  if (p->same) {
+    // stationary kernels: k(x,x) = outputscale (lazy_evaluated_kernel_tensor.py:107-133 evaluates kernel(diag=True))
+    fill_kernel<<<(unsigned)cdiv(p->row_count, 256), 256, 0, p->stream>>>(OUT, p->row_count, p->outputscale);
+  } else {
+    GP_REQUIRE(p->n1 == p->n2, GP_E_SHAPE, "diagonal of a %lld x %lld cross-covariance is undefined (kernel(x1, x2, diag=True) needs equal sizes)",
+               (long long)p->n1, (long long)p->n2);
+    const unsigned g = (unsigned)cdiv(p->n1, 256);
+    const float* Z1 = p->Z1.as<float>();
+    const float* Z2 = p->Z2.as<float>();
+    switch (p->kind) {
+      case GP_RBF: kdiag_cross_kernel<GP_RBF><<<g, 256, 0, p->stream>>>(Z1, Z2, p->DP, p->n1, p->outputscale, OUT); break;
+      case GP_MATERN12: kdiag_cross_kernel<GP_MATERN12><<<g, 256, 0, p->stream>>>(Z1, Z2, p->DP, p->n1, p->outputscale, OUT); break;
+      case GP_MATERN32: kdiag_cross_kernel<GP_MATERN32><<<g, 256, 0, p->stream>>>(Z1, Z2, p->DP, p->n1, p->outputscale, OUT); break;
+      default: kdiag_cross_kernel<GP_MATERN52><<<g, 256, 0, p->stream>>>(Z1, Z2, p->DP, p->n1, p->outputscale, OUT); break;
+    }
+  }
   p->launches++;
   GP_CUDA(cudaGetLastError());
   return GP_OK;

@@ -83,5 +83,9 @@ extern "C" int gp_slq_logdet(gp_plan* p, const float* TMAT, int n_tridiag, int l
   double s = 0.0;
   for (int i = 0; i < n_tridiag; ++i) s += h[i];
   *logdet_out = s;  // NaN tridiagonals propagate to a NaN log-det, as in InvQuadLogdet.forward
+  if (*reinterpret_cast<int*>(h + 64)) {
+    set_error("tridiagonal eigen-solver (implicit QL) did not converge within 100 sweeps for at least one probe; the SLQ log-determinant is unreliable");
+    return GP_W_EIG_NOT_CONVERGED;
+  }
   return GP_OK;
 }

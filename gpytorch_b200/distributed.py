@@ -17,10 +17,11 @@ from . import _lib
 def shard_rows(n: int, world: int, rank: int):
     """Equal row blocks (the all-gather needs equal counts): returns (row_begin, row_count, rows_per_rank).
     n must be divisible by world for the native path; `padded_size` gives the next valid n."""
-    per = (n + world - 1) // world
-    begin = min(rank * per, n)
-    count = max(0, min(per, n - begin))
-    return begin, count, per
+    if n % world:
+        raise ValueError(f"N={n} is not divisible by the world size {world}: the engine's all-gather needs equal row "
+                         f"shards (pad the problem to padded_size(n, world) = {padded_size(n, world)} rows)")
+    per = n // world
+    return rank * per, per, per
 
 
 def padded_size(n: int, world: int) -> int:

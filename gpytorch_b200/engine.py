@@ -59,13 +59,20 @@ class Plan:
         if comm is not None:
             check(self.lib.gp_plan_set_comm(self._h, comm.handle))
         self.comm = comm
+        self.refresh_data()
+        self.noise = 0.0
+        self.outputscale = 1.0
+
+    def refresh_data(self):
+        """(Re-)register the input buffers: the engine re-packs its tiles (centre / scale / 3xTF32 split) from the
+        CURRENT contents of x1 / x2.  Call after an in-place update of the inputs (operators._get_plan does, keyed on
+        the tensors' version counters)."""
         with torch.cuda.device(self.device):
             check(self.lib.gp_plan_set_data(
                 self._h, _ptr(self.x1), self.n1, self.x1.stride(0),
                 _ptr(None if self.same else self.x2), self.n2, self.x2.stride(0), self.d,
                 self.row_begin, self.row_count if self.row_count != self.n1 else 0))
-        self.noise = 0.0
-        self.outputscale = 1.0
+        return self
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -205,7 +212,7 @@ class Plan:
         st = self.lib.gp_mll(self._h, _ptr(y_minus_mean.contiguous()), _ptr(eps1), _ptr(eps2), _ptr(rademacher),
                              C.byref(opts), _ptr(solve), C.byref(res))
         check(st, warn=warn)
-        if res.status_flags & 2 and warn:
+        if res.status_flags & 6 and warn:   # bit 1: CG not converged, bit 2: SLQ eigen-solver not converged
             import warnings
             warnings.warn(_lib.last_error(), _lib.NumericalWarning)
         return res, solve

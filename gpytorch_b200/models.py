@@ -6,7 +6,6 @@ from . import settings
 from .distributions import MultivariateNormal
 from .likelihoods import GaussianLikelihood
 from .module import Module
-from .operators import KernelLinearOperator
 
 
 class ExactGP(Module):
@@ -38,34 +37,40 @@ class ExactGP(Module):
             return self.forward(*inputs, **kwargs)
         if self.train_inputs is None or self.train_targets is None:  # prior mode
             return self.forward(*inputs, **kwargs)
-        # posterior mode (exact_gp.py:293-333, DefaultPredictionStrategy)
+        # posterior mode (exact_gp.py:293-333, DefaultPredictionStrategy): the prior over the JOINT train + test inputs comes
+        # from the user's forward() (exact_gp.py:315-322) -- so input transforms, active_dims and any mean module apply to
+        # the test points exactly as they do in training -- and its blocks are taken by slicing the lazy covariance
+        # (lazy_evaluated_kernel_tensor.py:136-243 re-indexes x1 / x2; nothing is materialised).
         train_x, test_x = self.train_inputs[0], inputs[0]
+        n = train_x.size(-2)
         train_out = self.forward(train_x)
+        full_out = self.forward(torch.cat([train_x, test_x], dim=-2))
+        full_mean, full_covar = full_out.mean, full_out.lazy_covariance_matrix
         with settings._use_eval_tolerance(True):
             khat = self.likelihood(train_out).lazy_covariance_matrix
             if self._mean_cache is None:
                 resid = (self.train_targets - train_out.mean).unsqueeze(-1)
                 self._mean_cache = khat.solve(resid).squeeze(-1)  # exact_prediction_strategies.py:286
-            kop = train_out.lazy_covariance_matrix
-            k_star = KernelLinearOperator(test_x.contiguous(), train_x, kop.kind, kop.lengthscale, kop.outputscale)
-            test_mean = self.mean_module(test_x) + k_star.matmul(self._mean_cache)  # :396
-            k_ss = KernelLinearOperator(test_x.contiguous(), None, kop.kind, kop.lengthscale, kop.outputscale)
+            k_star = full_covar[n:, :n]                           # K(test, train)
+            k_ss = full_covar[n:, n:]
+            test_mean = full_mean[..., n:] + k_star.matmul(self._mean_cache)  # :396
+            m = test_x.size(-2)
+            dense = lambda a: a if torch.is_tensor(a) else a.to_dense()  # noqa: E731
             if settings.skip_posterior_variances.on():       # exact_prediction_strategies.py:432-433
-                covar = torch.zeros(test_x.size(0), test_x.size(0), device=test_x.device)
+                covar = torch.zeros(m, m, device=test_x.device)
             elif settings.fast_pred_var.on():                # LOVE: :268-272 (cache), :464-478 (use)
                 if self._covar_cache is None:
                     init = None
                     if settings.probe_seed.value() is not None:
                         g = torch.Generator(device="cpu").manual_seed(int(settings.probe_seed.value()))
-                        init = torch.randn(train_x.size(0), generator=g).to(train_x.device)
+                        init = torch.randn(n, generator=g).to(train_x.device)
                     self._covar_cache = khat.root_inv_decomposition(init).detach()   # [n, J], R R^T ~= K_hat^{-1}
                 root = k_star.matmul(self._covar_cache)      # covar_inv_quad_form_root, [m, J]
-                covar = k_ss.to_dense() - root @ root.transpose(-1, -2)
+                covar = dense(k_ss) - root @ root.transpose(-1, -2)
             else:
-                k_xs = KernelLinearOperator(train_x, test_x.contiguous(), kop.kind, kop.lengthscale, kop.outputscale)
-                rhs = k_xs.to_dense()                    # [n, m]
+                rhs = dense(full_covar[:n, n:])          # K(train, test) [n, m]
                 corr = k_star.matmul(khat.solve(rhs))    # exact predictive covariance, :435-462
-                covar = k_ss.to_dense() - corr
+                covar = dense(k_ss) - corr
         return MultivariateNormal(test_mean, covar)
 
     def set_train_data(self, inputs=None, targets=None, strict=True):

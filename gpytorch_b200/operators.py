@@ -39,9 +39,17 @@ def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
     key = (x1.data_ptr(), tuple(x1.shape), x1.stride(0), None if x2 is None else (x2.data_ptr(), tuple(x2.shape), x2.stride(0)),
            backend, str(x1.device), row_begin, row_count, id(comm))
     plan = _PLAN_CACHE.pop(key, None)
+    src_versions = (x1._version, None if x2 is None else x2._version)
+    if plan is not None and plan._src_versions != src_versions:
+        # same buffers, new contents (x.copy_(new), an optimiser step on the inputs, ...): the packed tiles are stale.
+        # torch bumps a tensor's version counter on every in-place write, so this is exact, not a heuristic.
+        plan.x1 = x1.contiguous()
+        plan.x2 = plan.x1 if x2 is None else x2.contiguous()
+        plan.refresh_data()
     if plan is None:
         plan = Plan(x1, x2, backend=backend, row_begin=row_begin, row_count=row_count, comm=comm)
         plan._hyp_key = None
+    plan._src_versions = src_versions
     _PLAN_CACHE[key] = plan  # most recently used last
     while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
         _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
@@ -60,12 +68,41 @@ class ConstantDiagLinearOperator:
         self.diag_value = diag_value
         self.n = int(diag_shape)
 
+    def __add__(self, other):
+        if isinstance(other, ConstantDiagLinearOperator):
+            return ConstantDiagLinearOperator(self.diag_value + other.diag_value, self.n)
+        if isinstance(other, DiagLinearOperator):
+            return other + self
+        return NotImplemented
+
     @property
     def shape(self):
         return torch.Size([self.n, self.n])
 
     def to_dense(self):
         return self.diag_value.reshape(()) * torch.eye(self.n, device=self.diag_value.device, dtype=self.diag_value.dtype)
+
+
+class DiagLinearOperator:
+    """diag(d) with a per-row vector d (FixedGaussianNoise, likelihoods/noise_models.py:150-190)."""
+
+    def __init__(self, diag: torch.Tensor):
+        self.diag_vec = diag
+        self.n = int(diag.shape[-1])
+
+    @property
+    def shape(self):
+        return torch.Size([self.n, self.n])
+
+    def to_dense(self):
+        return torch.diag_embed(self.diag_vec)
+
+    def __add__(self, other):
+        if isinstance(other, ConstantDiagLinearOperator):
+            return DiagLinearOperator(self.diag_vec + other.diag_value.reshape(-1)[:1])
+        if isinstance(other, DiagLinearOperator):
+            return DiagLinearOperator(self.diag_vec + other.diag_vec)
+        return NotImplemented
 
 
 class KernelLinearOperator:
@@ -83,15 +120,35 @@ class KernelLinearOperator:
         self.same = x2 is None or x2 is x1 or (x1.shape == x2.shape and x1.data_ptr() == x2.data_ptr())
 
     # -- plumbing --
-    def plan(self, noise: float = 0.0) -> Plan:
+    def _host_hypers(self, noise_t=None):
+        """(lengthscale list, outputscale, noise) as host floats with ONE device->host read per operator (cached: the
+        parameter tensors of an operator never change; a new forward builds a new operator)."""
+        cached = getattr(self, "_hyp_host", None)
+        if cached is None or (noise_t is not None and cached[3] is not noise_t):
+            parts = [self.lengthscale.detach().reshape(-1).float(), self.outputscale.detach().reshape(1).float()]
+            if noise_t is not None:
+                parts.append(noise_t.detach().reshape(-1)[:1].float())
+            vals = torch.cat(parts).tolist()
+            nl = self.lengthscale.numel()
+            cached = (vals[:nl], vals[nl], vals[nl + 1] if noise_t is not None else None, noise_t)
+            self._hyp_host = cached
+        return cached
+
+    def plan(self, noise=0.0) -> Plan:
+        """noise: a host float, or the device tensor of the likelihood (read together with the other hyper-parameters)."""
         fresh = False
         if self._plan is None:
             self._plan = _get_plan(self.x1, None if self.same else self.x2, settings.backend.value(),
                                    self._row_begin, self._row_count, self._comm)
             fresh = True
-        key = (self.kind, tuple(_as_list(self.lengthscale)), float(self.outputscale.detach()), float(noise))
+        if torch.is_tensor(noise):
+            ls, os_, nz, _ = self._host_hypers(noise)
+        else:
+            ls, os_, _, _ = self._host_hypers(None)
+            nz = float(noise)
+        key = (self.kind, tuple(ls), os_, nz)
         if fresh or getattr(self._plan, "_hyp_key", None) != key:
-            self._plan.set_hypers(self.kind, _as_list(self.lengthscale), float(self.outputscale.detach()), float(noise))
+            self._plan.set_hypers(self.kind, ls, os_, nz)
             self._plan._hyp_key = key
         return self._plan
 
@@ -169,10 +226,14 @@ class KernelLinearOperator:
 
     def to_dense(self):
         p = self.plan()
-        idx = torch.arange(self.x1.size(0), device=self.device)
+        idx = torch.arange(p.row_count, device=self.device)   # local rows of a row-sharded plan
         return p.rows(idx)
 
     def diagonal(self, dim1=-2, dim2=-1):
+        """kernel(x1, x2, diag=True) (lazy_evaluated_kernel_tensor.py:107-133): the constant outputscale for x2 == x1,
+        k(x1_i, x2_i) for a cross-covariance of equal sizes."""
+        if not self.same and self.x1.size(0) != self.x2.size(0):
+            raise RuntimeError(f"diagonal of a non-square operator {tuple(self.shape)} is undefined")
         return self.plan().diag()
 
     _diagonal = diagonal
@@ -273,8 +334,9 @@ class AddedDiagLinearOperator:
         return self
 
     def _plan(self) -> Plan:
-        self.kernel_op._last_noise = float(self.noise)
-        return self.kernel_op.plan(float(self.noise))
+        p = self.kernel_op.plan(self.diag.diag_value)
+        self.kernel_op._last_noise = p.noise
+        return p
 
     def matmul(self, rhs):
         return self.kernel_op.matmul(rhs) + self.noise * rhs

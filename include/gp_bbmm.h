@@ -36,7 +36,8 @@ enum {
   GP_W_NOT_CONVERGED = 4, /* CG hit max_iter above tolerance (NumericalWarning) */
   GP_W_PIVCHOL_NAN = 5,   /* NaN in pivoted Cholesky -> preconditioner dropped  */
   GP_E_NCCL = 6,
-  GP_E_STATE = 7          /* call order violated (data / hypers not set)      */
+  GP_E_STATE = 7,         /* call order violated (data / hypers not set)      */
+  GP_W_EIG_NOT_CONVERGED = 8 /* tridiagonal QL iteration hit its sweep limit: the SLQ log-det is unreliable (NumericalWarning) */
 };
 
 /* covariance function kinds: kernels/rbf_kernel.py:68-85, kernels/matern_kernel.py:85-110 */

@@ -131,15 +131,87 @@ def test_exact_gp_train_mode_guard():
 
 
 def test_shard_rows_cover_exactly():
-    for n, w in ((50000, 8), (200000, 8), (1001, 4), (7, 8)):
+    for n, w in ((50000, 8), (200000, 8), (1004, 4), (64, 8)):
         tot, prev_end = 0, 0
         for r in range(w):
             b, c, per = shard_rows(n, w, r)
-            assert b == prev_end or c == 0
+            assert b == prev_end and c == per == n // w
             prev_end = b + c
             tot += c
         assert tot == n
+    # unequal shards would hand ncclAllGather different counts per rank (hang / corruption): refused up front
+    for n, w in ((1001, 4), (7, 8)):
         assert padded_size(n, w) % w == 0 and padded_size(n, w) >= n
+        with pytest.raises(ValueError, match="not divisible"):
+            shard_rows(n, w, 0)
+        shard_rows(padded_size(n, w), w, w - 1)
+
+
+def test_bench_generators_match_the_oracle_generators_bitwise():
+    """bench.py's product arm imports nothing from oracle/; its input generators must still be the oracle's."""
+    import importlib.util
+    import os
+
+    import torch
+    from oracle import mll as om
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    x, y = bench.synthetic_problem(777, 5, 3)
+    xo, yo = om.synthetic_problem(777, 5, 3, torch.float32)
+    assert torch.equal(x, xo) and torch.equal(y, yo)
+    for a, b in zip(bench.make_probe_noise(500, 30, 10, 1), om.make_probe_noise(500, 30, 10, 1)):
+        assert torch.equal(a, b)
+    src = open(bench.__file__).read()
+    ours = src[src.index("def measure_workload"):src.index("def main()")]
+    assert "oracle" not in ours.replace("oracle port", "").replace("(oracle", "")   # the GPU arm never touches oracle/
+
+
+def test_state_dict_layout_matches_the_reference():
+    """Parameter / buffer names of a reference checkpoint (means/constant_mean.py: raw_constant; likelihoods/noise_models.py:
+    noise_covar.raw_noise; constraints/constraints.py:44-45: *_constraint.lower_bound / upper_bound)."""
+    import torch
+    import gpytorch_b200 as gp
+
+    class M(gp.models.ExactGP):
+        def __init__(self, x, y, lik):
+            super().__init__(x, y, lik)
+            self.mean_module = gp.means.ConstantMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel(ard_num_dims=2))
+
+        def forward(self, x):
+            return gp.distributions.MultivariateNormal(self.mean_module(x), self.covar_module(x))
+
+    lik = gp.likelihoods.GaussianLikelihood()
+    m = M(torch.rand(10, 2), torch.rand(10), lik)
+    keys = set(m.state_dict().keys())
+    want = {
+        "likelihood.noise_covar.raw_noise", "likelihood.noise_covar.raw_noise_constraint.lower_bound",
+        "likelihood.noise_covar.raw_noise_constraint.upper_bound", "mean_module.raw_constant",
+        "covar_module.raw_outputscale", "covar_module.base_kernel.raw_lengthscale",
+        "covar_module.base_kernel.raw_lengthscale_constraint.lower_bound",
+        "covar_module.base_kernel.raw_lengthscale_constraint.upper_bound",
+        "covar_module.raw_outputscale_constraint.lower_bound", "covar_module.raw_outputscale_constraint.upper_bound",
+    }
+    assert want <= keys, want - keys
+    assert tuple(m.state_dict()["covar_module.base_kernel.raw_lengthscale"].shape) == (1, 2)     # kernel.py:213-219
+    assert tuple(m.state_dict()["likelihood.noise_covar.raw_noise"].shape) == (1,)
+    assert tuple(m.state_dict()["mean_module.raw_constant"].shape) == ()
+    # a reference-shaped checkpoint loads strictly and lands in the right parameters
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["mean_module.raw_constant"] = torch.tensor(0.7)
+    sd["likelihood.noise_covar.raw_noise"] = torch.tensor([1.5])
+    m2 = M(torch.rand(10, 2), torch.rand(10), gp.likelihoods.GaussianLikelihood())
+    m2.load_state_dict(sd, strict=True)
+    assert float(m2.mean_module.constant) == pytest.approx(0.7)
+    assert float(m2.likelihood.noise) == pytest.approx(float(torch.nn.functional.softplus(torch.tensor(1.5)) + 1e-4))
+    # old layouts are renamed on load (constant_mean.py:18-31 does the same for `constant`)
+    sd_old = {k: v for k, v in sd.items() if k not in ("mean_module.raw_constant", "likelihood.noise_covar.raw_noise")}
+    sd_old["mean_module.constant"] = torch.tensor([0.25])
+    sd_old["likelihood.raw_noise"] = torch.tensor([0.5])
+    m2.load_state_dict(sd_old, strict=True)
+    assert float(m2.mean_module.constant) == pytest.approx(0.25)
 
 
 def test_oracle_love_root_reproduces_inverse_on_small_system():
