@@ -498,7 +498,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   GP_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   GP_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   const int first_stop = std::max(std::min(10, max_iter - 1), n_tridiag ? std::min(n_tridiag_iter, max_iter - 1) : 0);
-  const int64_t rows_pad = cdiv(n, TILE_I) * TILE_I;
+  const int64_t rows_pad = p->rows_pad;
   int status = GP_OK;
   int kk = 0;
   bool finished = false;

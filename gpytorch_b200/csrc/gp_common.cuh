@@ -126,6 +126,9 @@ struct gp_plan {
   int nsplit = 1;  // column splits of the K.V work (load balance over 148 SMs)
   int nparts = 1;  // partial-sum slots written by the K.V kernel (nsplit, x2 for the tcgen05 kernel)
   int64_t ntile_i = 0, ntile_j = 0, tiles_per_split = 0;
+  int64_t rows_pad = 0;  // local rows padded to the 256-row CTA block of the tcgen05 kernel: pitch of `partial`, rows of XA
+  bool tc2 = false;      // second-generation tcgen05 kernel (kmv_tc2.cu); the round-1 kernel (kmv_tc.cu) serves KP > 64
+  int npoly = 2;         // of every 8 ex2 evaluations, how many run as a polynomial on the FMA pipe (0, 2, 4)
   // device buffers
   int* xbad = nullptr;  // device flag: non-finite value in the packed inputs (lives behind mean[])
   gp::DevBuf mean, scale, Z1, Z2, XA, XB, V16, Vtiles, partial, out16;
@@ -144,6 +147,7 @@ int to_v16(gp_plan* p, const float* V, int64_t ldv, int t, int64_t n, float* V16
 int pack_v_tiles(gp_plan* p, const float* V16);                         // pack.cu (tcgen05 B operand of GEMM2)
 int kmv_partials(gp_plan* p, const float* V16, const int* done_flag);   // dispatch simt / tcgen05
 int kmv_tc_launch_kind(gp_plan* p, int kind, const int* done_flag);     // kind may be GP_DERIV + kind
+int kmv_tc2_launch_kind(gp_plan* p, int kind, const int* done_flag);    // kmv_tc2.cu
 int kmv_simt_launch(gp_plan* p, const float* V16, const int* done_flag);
 int kmv_tc_launch(gp_plan* p, const int* done_flag);
 int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t, int add_noise);

@@ -71,7 +71,7 @@ template <int KIND>
 static int launch_simt_kind(gp_plan* p, const float* V16, const int* done_flag) {
   const float* Z1 = p->same ? p->Z2.as<float>() + p->row_begin * p->DP : p->Z1.as<float>();
   const float* Z2 = p->Z2.as<float>();
-  int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
+  int64_t rows_pad = p->rows_pad;
   dim3 grid((unsigned)cdiv(p->row_count, SIMT_TI), (unsigned)p->nsplit);
   int64_t cps = p->tiles_per_split * SIMT_TJ;
 #define GP_SIMT_CASE(D)                                                                                          \
@@ -130,7 +130,7 @@ __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int ns
 }
 
 int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t, int add_noise) {
-  int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
+  int64_t rows_pad = p->rows_pad;
   int64_t tot = p->row_count * TP;
   float na = (add_noise && p->same) ? p->noise : 0.f;
   kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count,
@@ -385,7 +385,7 @@ extern "C" int gp_bilinear_grad(gp_plan* p, const float* Lf, int64_t ldl, const 
   // the fused K.V kernel (f = k, then f = g = l dk/dl through the derivative kinds) + a dot product with L.  ARD needs d
   // weighted sums per pair and stays on the SIMT kernel.
   const bool use_tc = !ard && p->backend == GP_BACKEND_TCGEN05;
-  const int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
+  const int64_t rows_pad = p->rows_pad;
   const int dot_blocks = (int)std::min<int64_t>(nblk, 2 * p->n_sm);
   for (int c0 = 0; c0 < s; c0 += TP) {
     int tc = std::min(TP, s - c0);

@@ -367,7 +367,7 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
     GP_CUDA(cudaFuncSetAttribute(kmv_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[dev_slot] = true;
   }
-  int64_t rows_pad = p->ntile_i * TILE_I;
+  int64_t rows_pad = p->rows_pad;
   dim3 grid((unsigned)p->ntile_i, (unsigned)p->nsplit);
   kmv_tc_kernel<KIND><<<grid, TC_THREADS, smem_bytes, p->stream>>>(
       p->XA.as<float>(), p->XB.as<float>(), p->Vtiles.as<float>(), p->partial.as<float>(), p->KP, ns, p->ntile_j,
@@ -378,6 +378,7 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
 }
 
 int kmv_tc_launch_kind(gp_plan* p, int kind, const int* done_flag) {
+  if (p->tc2) return kmv_tc2_launch_kind(p, kind, done_flag);
   switch (kind) {
     case GP_RBF: return launch_tc_kind<GP_RBF>(p, done_flag);
     case GP_MATERN12: return launch_tc_kind<GP_MATERN12>(p, done_flag);

@@ -13,6 +13,8 @@
 //   XB   [ntile_j][KP/4][ 64][4]   B operand  [z_hi | z_hi | z_lo | 1 1 n_hi n_lo | 0..]
 //   so that  sum_k A_ik B_jk = z_i.z_j (to ~2^-22) + n_i + n_j,  n = -0.5 |z|^2  = a_ij.
 //   Vt   per 64-row tile: [64/4][32][4] tf32 (rows 0-15 hi, 16-31 lo) + [64/8][16][8] bf16  (B operands of GEMM2)
+#include <stdlib.h>
+
 #include "gp_common.cuh"
 
 namespace gp {
@@ -147,10 +149,17 @@ int choose_geometry(gp_plan* p) {
   GP_REQUIRE(!(want == GP_BACKEND_TCGEN05 && p->KP > KP_MAX), GP_E_SHAPE,
              "tcgen05 backend needs 3d+4 <= %d (d=%d)", KP_MAX, p->d);
   p->backend = want;
-  p->ntile_i = cdiv(p->row_count, TILE_I);
+  p->rows_pad = cdiv(p->row_count, 2 * TILE_I) * 2 * TILE_I;
+  p->ntile_i = p->rows_pad / TILE_I;
   p->ntile_j = cdiv(p->n2, TILE_J);
+  p->tc2 = p->backend == GP_BACKEND_TCGEN05 && p->KP <= 64 && getenv("GP_KMV_V1") == nullptr;
+  {
+    const char* e = getenv("GP_NPOLY");
+    p->npoly = e ? atoi(e) : 2;
+    if (p->npoly != 0 && p->npoly != 2 && p->npoly != 4) p->npoly = 2;
+  }
   // column splits: pick the smallest nsplit whose unit count fills the SMs best
-  int64_t nti = (p->backend == GP_BACKEND_TCGEN05) ? p->ntile_i : cdiv(p->row_count, SIMT_TI);
+  int64_t nti = (p->backend == GP_BACKEND_TCGEN05) ? (p->tc2 ? p->rows_pad / (2 * TILE_I) : p->ntile_i) : cdiv(p->row_count, SIMT_TI);
   int64_t ntj = (p->backend == GP_BACKEND_TCGEN05) ? p->ntile_j : cdiv(p->n2, SIMT_TJ);
   int best = 1;
   double best_eff = -1.0;
@@ -159,7 +168,7 @@ int choose_geometry(gp_plan* p) {
     int64_t per = cdiv(ntj, s);
     if (s > 1 && per < 8) break;  // keep units long enough to amortise the prologue
     int64_t units = nti * s;
-    const int64_t slots = (int64_t)p->n_sm * (p->backend == GP_BACKEND_TCGEN05 ? 2 : 1);  // resident CTAs
+    const int64_t slots = (int64_t)p->n_sm * ((p->backend == GP_BACKEND_TCGEN05 && !p->tc2) ? 2 : 1);  // resident CTAs
     int64_t waves = cdiv(units, slots);
     double eff = (double)(nti * ntj) / (double)(waves * slots * per);
     if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
@@ -207,7 +216,7 @@ int pack_inputs(gp_plan* p) {
   }
   if (p->backend == GP_BACKEND_TCGEN05) {
     const int KP = p->KP;
-    int64_t padA = p->ntile_i * TILE_I, padB = p->ntile_j * TILE_J;
+    int64_t padA = p->rows_pad, padB = p->ntile_j * TILE_J;
     GP_CHECK(p->XA.ensure(sizeof(float) * padA * KP));
     GP_CHECK(p->XB.ensure(sizeof(float) * padB * KP));
     const float* ZA = p->same ? p->Z2.as<float>() : p->Z1.as<float>();
@@ -217,9 +226,8 @@ int pack_inputs(gp_plan* p) {
     p->launches += 2;
     GP_CHECK(p->Vtiles.ensure(sizeof(float) * p->ntile_j * (2 * TILE_J * TP + TILE_J * TP / 2)));
   }
-  int64_t rows_pad = cdiv(p->row_count, TILE_I) * TILE_I;
   p->nparts = p->nsplit;
-  GP_CHECK(p->partial.ensure(sizeof(float) * (size_t)p->nparts * rows_pad * TP));
+  GP_CHECK(p->partial.ensure(sizeof(float) * (size_t)p->nparts * p->rows_pad * TP));
   GP_CUDA(cudaGetLastError());
   return GP_OK;
 }
