@@ -24,7 +24,8 @@
 //   slot (w, b) at (2w + b) * 96: S / P_hi [0,64) + P_lo (bf16 pairs) [64,96)        -> [0, 384)
 //   O(w) at 384 + 16 w                                                               -> [384, 416)
 //   A(w) at 416 + 48 w  (TS mode, KP <= 48)                                          -> [416, 512)
-// Warp roles: 0-3 epilogue warpgroup 0, 4-7 epilogue warpgroup 1, 8 TMA producer, 9 TMEM allocator + MMA issuer.
+// Warp roles: 0-3 epilogue warpgroup 0, 4-7 epilogue warpgroup 1, 8 TMA producer, 9 / 10 MMA issuers of warpgroup 0 / 1
+// (warp 9 also allocates TMEM).
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,8 +35,10 @@ using namespace ptx;
 
 namespace v2 {
 
-constexpr int THREADS = 320;
-constexpr int W_PROD = 8, W_MMA = 9;
+constexpr int THREADS = 640;
+constexpr int W_MMA = 0, W_PROD = 2, W_EPI = 4;   // warps 0 / 1 MMA issuers (0 also allocates TMEM), 2 TMA producer, 3 idle, 4-19 epilogue.
+// The issuers are the OLDEST warps of their sub-partitions: with them at the highest warp ids the epilogue warps won the issue
+// arbitration most of the time and one tile's ~110 issuer instructions took ~1200 cycles (profiles/NOTES_r02.md)
 constexpr int SLOT_COLS = 96;                  // S / P_hi 64 + P_lo 32
 constexpr int COL_O = 4 * SLOT_COLS;           // 384
 constexpr int COL_A = COL_O + 2 * TP;          // 416
@@ -53,7 +56,7 @@ struct Bars {
   uint64_t b_full[MAX_NS];
   uint64_t b_empty[MAX_NS];    // 2 arrivals: GEMM2(0,u) and GEMM2(1,u) have read the stage
   uint64_t s_full[2][2];       // [warpgroup][slot]
-  uint64_t p_full[2][2];       // 128 arrivals
+  uint64_t p_full[2][2];       // 256 arrivals (8 warps)
   uint64_t o_full[2];          // [warpgroup]
   uint32_t tmem_base;
   uint32_t pad;
@@ -169,16 +172,17 @@ __device__ __forceinline__ void split_group8(const float (&p)[8], uint32_t* __re
 // One pipeline step.  On entry: pc = P of the group to be stored (MUFU issued one step ago), sn = S of the group that goes
 // through the MUFU now (its load was issued one step ago).  (1) wait for sn, apply the exact-diagonal fix-up, (2) put the
 // load of the group after that in flight into sn2 (address t_ld), (3) MUFU / polynomial on sn -> pn, (4) split pc and store.
-template <int KIND, int NPOLY, bool DO_LOAD>
+template <int KIND, int NPOLY, int NLOAD>
 __device__ __forceinline__ void epi_step(uint32_t t_st_hi, uint32_t t_st_lo, uint32_t t_ld, const float (&pc)[8], uint32_t (&sn)[8],
-                                         float (&pn)[8], uint32_t (&sn2)[8], bool diag, int cd_rel) {
+                                         float (&pn)[8], uint32_t (&sn2)[8], uint32_t (&sn3)[8], bool diag, int cd_rel) {
   tmem_wait_ld();
   if (diag) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i == cd_rel) sn[i] = 0u;   // a_ii = 0 exactly (kernel.py:44-45 fills the diagonal with 0)
   }
-  if (DO_LOAD) GP_TMEM_LD8(t_ld, sn2);
+  if (NLOAD >= 1) GP_TMEM_LD8(t_ld, sn2);
+  if (NLOAD >= 2) GP_TMEM_LD8(t_ld + 8, sn3);
   cov_group8<KIND, NPOLY>(sn, pn);
   uint32_t hi[8], lo[4];
   split_group8(pc, hi, lo);
@@ -186,14 +190,14 @@ __device__ __forceinline__ void epi_step(uint32_t t_st_hi, uint32_t t_st_lo, uin
   GP_TMEM_ST4(t_st_lo, lo);
 }
 
-template <int KIND, int NPOLY, bool A_TMEM>
+template <int KIND, int NPOLY, bool A_TMEM, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const float* __restrict__ Vt,
                float* __restrict__ partial, int KP, int NS, int64_t ntile_j, int64_t tiles_per_split, int64_t rows_pad,
                int same, int64_t row_begin, const int* __restrict__ done_flag, long long* __restrict__ trace) {
   if (done_flag && *done_flag) return;  // CTA-uniform, before any barrier / TMEM state exists
-  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-#define GP_TR2(tile, ev) do { if (tr && lane == 0 && (tile) < 256) trace[(tile) * 8 + (ev)] = clock64(); } while (0)
+  const bool tr = TRACE && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define GP_TR2(tile, ev) do { if (TRACE && tr && lane == 0 && (tile) < 256) trace[(tile) * 16 + (ev)] = clock64(); } while (0)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = (int)warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -211,7 +215,7 @@ kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const
   Bars* bars = reinterpret_cast<Bars*>(sA + (A_TMEM ? 0 : 2 * a_bytes));
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bars->a_full), A_TMEM ? 256 : 1);
+    mbar_init(smem_u32(&bars->a_full), A_TMEM ? 512 : 1);
     for (int s = 0; s < MAX_NS; ++s) {
       mbar_init(smem_u32(&bars->b_full[s]), 1);
       mbar_init(smem_u32(&bars->b_empty[s]), 2);
@@ -219,7 +223,7 @@ kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const
     for (int w = 0; w < 2; ++w) {
       for (int b = 0; b < 2; ++b) {
         mbar_init(smem_u32(&bars->s_full[w][b]), 1);
-        mbar_init(smem_u32(&bars->p_full[w][b]), 128);
+        mbar_init(smem_u32(&bars->p_full[w][b]), 256);
       }
       mbar_init(smem_u32(&bars->o_full[w]), 1);
     }
@@ -251,94 +255,149 @@ kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const
         if (++sb == NS) { sb = 0; par ^= 1; }
       }
     }
-  } else if (warp == W_MMA) {
-    // ===================== MMA issuer (converged warp, one elected lane issues each batch) ==========
-    // Program order:  G1(0,0) G1(1,0) G1(0,1) G1(1,1) ; for u: for w: wait P(w,u) -> GEMM2(w,u) -> GEMM1(w,u+2).
-    // One thread issues everything, so the tensor pipe orders GEMM2(w,u) (reads P in slot u&1) before GEMM1(w,u+2)
-    // (overwrites it) and GEMM2(w,u) (overwrites O(w)) after the epilogue's arrive on p_full(w,u), which follows its
-    // fold of O(w) from tile u-1.
+  } else if (warp < 2) {
+    // ===================== MMA issuers: warp 9 serves warpgroup 0, warp 10 warpgroup 1 ==========
+    // Program order per issuer:  G1(w,0) G1(w,1) ; for u: wait P(w,u) -> GEMM2(w,u) -> GEMM1(w,u+2).
+    // One thread issues everything of a warpgroup, so the tensor pipe orders GEMM2(w,u) (reads P in slot u&1) before
+    // GEMM1(w,u+2) (overwrites it), and GEMM2(w,u) (overwrites O(w)) comes after the epilogue's arrive on p_full(w,u), which
+    // follows its fold of O(w) from tile u-1.  Two issuers because the per-tile scalar work of ONE warp (descriptor updates,
+    // two barrier polls, three commits, 25 MMAs: ~1000 cycles of dependent-issue latency, profiles/NOTES_r02.md) was the
+    // bottleneck of the first version of this kernel; everything that can be is a running value updated by constant adds.
+    const int w = warp;
     if (T > 0) {
       constexpr uint32_t IDESC1 = idesc_tf32(TILE_I, TILE_J);    // S = A B^T               128 x 64
       constexpr uint32_t IDESC2A = idesc_tf32(TILE_I, TP);       // O (+)= P_hi V_hi^T / V_lo^T   (tf32) 128 x 16
       constexpr uint32_t IDESC2B = idesc_bf16(TILE_I, TP);       // O += P_lo V^T           (bf16) 128 x 16
       const int ksteps1 = KP / 8;
+      const uint32_t stage_d = stage_bytes >> 4;                 // descriptor units
+      const uint64_t bdesc_first = smem_desc(smem_u32(sStage), TILE_J * 16, 128);
+      const uint64_t vdesc_first = smem_desc(smem_u32(sStage + b_bytes), 2 * TP * 16, 128);            // tf32 tile: rows 0-15 V_hi, 16-31 V_lo
+      const uint64_t wdesc_first = smem_desc(smem_u32(sStage + b_bytes + V_TF32_BYTES), TP * 16, 128);  // bf16 tile, 16 rows
+      const uint64_t a_desc0 = smem_desc(smem_u32(sA + (size_t)w * a_bytes), TILE_I * 16, 128);
+      const uint32_t a_t = tmem + (uint32_t)(COL_A + w * A_COLS_MAX);
+      const uint32_t slot0 = tmem + (uint32_t)((2 * w) * SLOT_COLS);
+      const uint32_t d_o = tmem + (uint32_t)(COL_O + w * TP);
+      const uint32_t ofull = smem_u32(&bars->o_full[w]);
+      const uint32_t bfull0 = smem_u32(&bars->b_full[0]), bempty0 = smem_u32(&bars->b_empty[0]);
+      const uint32_t sfull0 = smem_u32(&bars->s_full[w][0]), pfull0 = smem_u32(&bars->p_full[w][0]);
       mbar_wait(smem_u32(&bars->a_full), 0);
       tc_fence_after();
-      auto issue_g1 = [&](int w, int u) {
-        const int sb = u % NS;
-        mbar_wait(smem_u32(&bars->b_full[sb]), (uint32_t)((u / NS) & 1));
+      // running state of the GEMM1 stream (tile g1): ring stage, its parity, descriptor of its B tile
+      int g1 = 0, sb1 = 0;
+      uint32_t par1 = 0;
+      uint64_t bdesc1 = bdesc_first;
+      auto issue_g1 = [&]() {
+        mbar_poll(bfull0 + 8u * (uint32_t)sb1, par1);
         tc_fence_after();
-        if (w == 0) GP_TR2(u, 0);
-        const uint64_t b_desc0 = smem_desc(smem_u32(sStage + (size_t)sb * stage_bytes), TILE_J * 16, 128);
-        const uint32_t d_s = tmem + (uint32_t)((2 * w + (u & 1)) * SLOT_COLS);
-        const uint32_t sfull = smem_u32(&bars->s_full[w][u & 1]);
-        const uint32_t a_t = tmem + (uint32_t)(COL_A + w * A_COLS_MAX);
-        const uint64_t a_desc0 = smem_desc(smem_u32(sA + (size_t)w * a_bytes), TILE_I * 16, 128);
+        if (w == 0 && g1 >= 2) GP_TR2(g1 - 2, 10);
+        const uint32_t d_s = slot0 + (uint32_t)((g1 & 1) * SLOT_COLS);
+        const uint32_t sfull = sfull0 + 8u * (uint32_t)(g1 & 1);
         if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // fully unrolled + predicated: every operand stays in uniform registers
-            if (ks < ksteps1) {
-              if (A_TMEM) mma_tf32_ts_1t(d_s, a_t + ks * 8, b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)), IDESC1, ks > 0 ? 1u : 0u);
-              else mma_tf32_ss_1t(d_s, a_desc0 + (uint64_t)(ks * ((2 * TILE_I * 16) >> 4)), b_desc0 + (uint64_t)(ks * ((2 * TILE_J * 16) >> 4)), IDESC1, ks > 0 ? 1u : 0u);
+          // a REAL loop over the k-steps with running operands (4 instructions per MMA); the unrolled-and-predicated and the
+          // switch-per-count forms cost the issuer ~500 cycles per tile
+          uint64_t bd = bdesc1;
+          if (A_TMEM) {
+            uint32_t aa = a_t;
+            mma_tf32_ts_1t(d_s, aa, bd, IDESC1, 0u);
+#pragma unroll 1
+            for (int ks = 1; ks < ksteps1; ++ks) {
+              aa += 8;
+              bd += (uint64_t)((2 * TILE_J * 16) >> 4);
+              mma_tf32_ts_1t(d_s, aa, bd, IDESC1, 1u);
             }
+          } else {
+            uint64_t ad = a_desc0;
+            mma_tf32_ss_1t(d_s, ad, bd, IDESC1, 0u);
+#pragma unroll 1
+            for (int ks = 1; ks < ksteps1; ++ks) {
+              ad += (uint64_t)((2 * TILE_I * 16) >> 4);
+              bd += (uint64_t)((2 * TILE_J * 16) >> 4);
+              mma_tf32_ss_1t(d_s, ad, bd, IDESC1, 1u);
+            }
+          }
           tc_commit_1t(sfull);
         }
         __syncwarp();
+        ++g1;
+        bdesc1 += stage_d;
+        if (++sb1 == NS) { sb1 = 0; par1 ^= 1; bdesc1 = bdesc_first; }
       };
-      for (int u0 = 0; u0 < 2 && u0 < T; ++u0) {
-        issue_g1(0, u0);
-        issue_g1(1, u0);
-      }
-      for (int u = 0; u < T; ++u) {
-        const int sb2 = u % NS;
-        const uint32_t v_addr = smem_u32(sStage + (size_t)sb2 * stage_bytes + b_bytes);
-        const uint64_t v_desc0 = smem_desc(v_addr, 2 * TP * 16, 128);                 // tf32 tile: rows 0-15 V_hi, 16-31 V_lo
-        const uint64_t w_desc0 = smem_desc(v_addr + V_TF32_BYTES, TP * 16, 128);      // bf16 tile, 16 rows
-        const uint32_t bempty = smem_u32(&bars->b_empty[sb2]);
+      issue_g1();
+      if (T > 1) issue_g1();
+      // running state of the GEMM2 stream (tile u)
+      int sb2 = 0;
+      uint64_t vdesc = vdesc_first, wdesc = wdesc_first;
+      uint32_t ppar = 0;
 #pragma unroll 1
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(smem_u32(&bars->p_full[w][u & 1]), (uint32_t)((u >> 1) & 1));
-          tc_fence_after();
-          if (w == 0) GP_TR2(u, 1);
-          const uint32_t p_hi = tmem + (uint32_t)((2 * w + (u & 1)) * SLOT_COLS);
-          const uint32_t p_lo = p_hi + TILE_J;
-          const uint32_t d_o = tmem + (uint32_t)(COL_O + w * TP);
-          const uint32_t ofull = smem_u32(&bars->o_full[w]);
-          if (elect_one()) {
+      for (int u = 0; u < T; ++u) {
+        const uint32_t b = (uint32_t)(u & 1);
+        mbar_poll(pfull0 + 8u * b, ppar);
+        tc_fence_after();
+        GP_TR2(u, w == 0 ? 1 : 6);
+        const uint32_t p_hi = slot0 + b * SLOT_COLS;
+        const uint32_t p_lo = p_hi + TILE_J;
+        const uint32_t bempty = bempty0 + 8u * (uint32_t)sb2;
+        if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TILE_J / 8; ++ks) {
-              const uint64_t vd = v_desc0 + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4));
-              mma_tf32_ts_1t(d_o, p_hi + ks * 8, vd, IDESC2A, ks > 0 ? 1u : 0u);                 // V_hi rows
-              mma_tf32_ts_1t(d_o, p_hi + ks * 8, vd + (uint64_t)((TP * 16) >> 4), IDESC2A, 1u);   // V_lo rows (+256 B)
-            }
-#pragma unroll
-            for (int ks = 0; ks < TILE_J / 16; ++ks)
-              mma_bf16_ts_1t(d_o, p_lo + ks * 8, w_desc0 + (uint64_t)(ks * ((2 * TP * 16) >> 4)), IDESC2B, 1u);
-            tc_commit_1t(bempty);   // (one of two arrivals) this warpgroup's GEMM2 has read the V stage
-            tc_commit_1t(ofull);    // O(w) holds tile u's product
+          for (int ks = 0; ks < TILE_J / 8; ++ks) {
+            const uint64_t vd = vdesc + (uint64_t)(ks * ((2 * 2 * TP * 16) >> 4));
+            mma_tf32_ts_1t(d_o, p_hi + ks * 8, vd, IDESC2A, ks > 0 ? 1u : 0u);                 // V_hi rows
+            mma_tf32_ts_1t(d_o, p_hi + ks * 8, vd + (uint64_t)((TP * 16) >> 4), IDESC2A, 1u);   // V_lo rows (+256 B)
           }
-          __syncwarp();
-          if (u + 2 < T) issue_g1(w, u + 2);   // refill the slot GEMM2(w,u) has just consumed (same thread => ordered)
+#pragma unroll
+          for (int ks = 0; ks < TILE_J / 16; ++ks)
+            mma_bf16_ts_1t(d_o, p_lo + ks * 8, wdesc + (uint64_t)(ks * ((2 * TP * 16) >> 4)), IDESC2B, 1u);
+          tc_commit_1t(bempty);   // (one of two arrivals) this warpgroup's GEMM2 has read the V stage
+          tc_commit_1t(ofull);    // O(w) holds tile u's product
+        }
+        __syncwarp();
+        if (w == 0) GP_TR2(u, 9);
+        ppar ^= b;                // the parity of p_full[w][b] flips every second tile
+        vdesc += stage_d;
+        wdesc += stage_d;
+        if (++sb2 == NS) { sb2 = 0; vdesc = vdesc_first; wdesc = wdesc_first; }
+        if (g1 < T) issue_g1();   // refill the slot GEMM2(w,u) has just consumed (same thread => ordered)
+        if (w == 0) GP_TR2(u, 7);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== observer (trace runs only): when do S(0,u) and O(0,u) really complete? =====================
+    if (tr && T > 0) {
+      if (lane == 0) {
+        for (int u = 0; u < T && u < 256; ++u) {
+          mbar_wait(smem_u32(&bars->s_full[0][u & 1]), (uint32_t)((u >> 1) & 1));
+          trace[u * 16 + 0] = clock64();
+        }
+      } else if (lane == 1) {
+        for (int u = 0; u < T && u < 256; ++u) {
+          mbar_wait(smem_u32(&bars->o_full[0]), (uint32_t)(u & 1));
+          trace[u * 16 + 8] = clock64();
         }
       }
     }
-  } else {
-    // ===================== epilogue warpgroups (warps 0-3: rows [0,128), warps 4-7: rows [128,256) of the block) =========
-    const int wg = warp >> 2;
-    const int q = warp & 3;            // TMEM lane quadrant of this warp
+  } else if (warp >= W_EPI) {
+    // ===================== epilogue warps: 16 = 2 warpgroups (row halves) x 2 column halves x 4 lane quadrants =========
+    // epilogue warp i = warp - 4: warpgroup wg = i >> 3 (rows [128 wg, +128) of the block), column half h = (i >> 2) & 1 (columns [32 h, +32) of
+    // every 64-column tile, and columns [8 h, +8) of O), lane quadrant q = i & 3.  Four warps per SM sub-partition hide the
+    // TMEM-load / MUFU / TMEM-store latencies of one another (with two, the first version ran at half the MUFU rate).
+    const int wg = (warp - W_EPI) >> 3;
+    const int h = ((warp - W_EPI) >> 2) & 1;
+    const int q = warp & 3;            // TMEM lane quadrant of this warp (warp % 4)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int64_t rloc = ip * ROWS_CTA + wg * TILE_I + q * 32 + lane;   // local (padded) row of this thread
     const int64_t gi = row_begin + rloc;                                // global row
-    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * TP);
-    const uint32_t t_slot0 = tmem + lane_off + (uint32_t)((2 * wg) * SLOT_COLS);
+    const uint32_t t_o = tmem + lane_off + (uint32_t)(COL_O + wg * TP + h * 8);
+    const uint32_t t_slot0 = tmem + lane_off + (uint32_t)((2 * wg) * SLOT_COLS + h * 32);       // this warp's S / P_hi columns
+    const uint32_t t_lo0 = tmem + lane_off + (uint32_t)((2 * wg) * SLOT_COLS + TILE_J + h * 16);  // ... and P_lo columns
     if (A_TMEM) {
-      // this thread's row of the A tile: XA[tile][kc][row][4] -> TMEM columns COL_A + 48 wg + [0, KP)
+      // this thread's row of the A tile: XA[tile][kc][row][4] -> TMEM columns COL_A + 48 wg + [0, KP); the two column halves
+      // of a warpgroup store alternate 8-column blocks
       const float4* src = reinterpret_cast<const float4*>(XA + (ip * 2 + wg) * (int64_t)TILE_I * KP) + (q * 32 + lane);
       const uint32_t t_a = tmem + lane_off + (uint32_t)(COL_A + wg * A_COLS_MAX);
       if (T > 0) {
 #pragma unroll
         for (int k8 = 0; k8 < A_COLS_MAX / 8; ++k8) {
-          if (k8 * 8 < KP) {
+          if (k8 * 8 < KP && (k8 & 1) == h) {
             const float4 v0 = __ldg(src + (size_t)(2 * k8) * TILE_I), v1 = __ldg(src + (size_t)(2 * k8 + 1) * TILE_I);
             uint32_t r[8] = {__float_as_uint(v0.x), __float_as_uint(v0.y), __float_as_uint(v0.z), __float_as_uint(v0.w),
                              __float_as_uint(v1.x), __float_as_uint(v1.y), __float_as_uint(v1.z), __float_as_uint(v1.w)};
@@ -352,93 +411,81 @@ kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const
     }
     // O is folded into fp32 registers after EVERY tile: the tensor core's accumulator truncates on each add, so long
     // TMEM accumulation chains drift (1e-4 at N = 50k); 20 adds per tile keep the product at fp32 level.
-    float acc[TP];
+    float acc[8];
 #pragma unroll
-    for (int c = 0; c < TP; ++c) acc[c] = 0.f;
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
     if (T > 0) {
-      uint32_t sa[8], sb[8];
+      // S of column group g (8 columns) of the current tile lives in register set g & 3: four sets, so a load never has to
+      // wait for the MUFU ops that still read the set it overwrites.  P alternates between pa / pb.
+      uint32_t s0[8], s1[8], s2[8], s3[8];
       float pa[8], pb[8];
       auto tile_diag = [&](int u, int& cd) -> bool {
-        const int64_t jbase = (jt0 + u) * TILE_J;
+        const int64_t jbase = (jt0 + u) * TILE_J + h * 32;             // first column of this warp's half tile
         const int64_t r0 = row_begin + ip * ROWS_CTA + wg * TILE_I;
         cd = (int)max((int64_t)-1000000, min((int64_t)1000000, gi - jbase));
-        return same && (r0 < jbase + TILE_J) && (jbase < r0 + TILE_I);
+        return same && (r0 < jbase + 32) && (jbase < r0 + TILE_I);
       };
-      // ---- prologue: S(0) of tile 0 through the MUFU, S(1) in flight ----
-      int cd;
-      bool diag = tile_diag(0, cd);
-      mbar_wait(smem_u32(&bars->s_full[wg][0]), 0);
-      tc_fence_after();
-      GP_TMEM_LD8(t_slot0, sa);
-      tmem_wait_ld();
-      if (diag) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i == cd) sa[i] = 0u;
-      }
-      GP_TMEM_LD8(t_slot0 + 8, sb);
-      cov_group8<KIND, NPOLY>(sa, pa);
+      // No prefetch across tiles: S(u+1) is asked for only after P(u) has been released.  GEMM1(wg, u+1) can start no earlier
+      // than the release of P(u-1) (it overwrites that slot) and, with the issuer's ~1000-cycle turn-around, needs the whole
+      // time the warpgroup spends on tile u; the bubble at the start of a tile is filled by the other three warps of the
+      // SM sub-partition.
+#pragma unroll 1
       for (int u = 0; u < T; ++u) {
         const int b = u & 1;
         const uint32_t t_s = t_slot0 + (uint32_t)(b * SLOT_COLS);       // S, overwritten in place by P_hi
-        const uint32_t t_lo = t_s + TILE_J;
-        if (q == 0) GP_TR2(u, 2 + wg);
-        // steps 0..5: everything stays inside this tile
-#pragma unroll 1
-        for (int g = 0; g < 6; g += 2) {
-          epi_step<KIND, NPOLY, true>(t_s + 8 * g, t_lo + 4 * g, t_s + 8 * (g + 2), pa, sb, pb, sa, diag, cd - 8 * (g + 1));
-          epi_step<KIND, NPOLY, true>(t_s + 8 * (g + 1), t_lo + 4 * (g + 1), t_s + 8 * (g + 3), pb, sa, pa, sb, diag, cd - 8 * (g + 2));
+        const uint32_t t_lo = t_lo0 + (uint32_t)(b * SLOT_COLS);
+        int cd;
+        const bool diag = tile_diag(u, cd);
+        mbar_wait(smem_u32(&bars->s_full[wg][b]), (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        if (q == 0 && h == 0) GP_TR2(u, 2 + wg);
+        GP_TMEM_LD8(t_s, s0);
+        GP_TMEM_LD8(t_s + 8, s1);
+        tmem_wait_ld();
+        if (diag) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == cd) s0[i] = 0u;
         }
-        // steps 6, 7: the loads (and the last MUFU group) belong to the NEXT tile, which lives in the other slot
-        const bool has_next = u + 1 < T;
-        int cdn = 0;
-        const bool diagn = has_next ? tile_diag(u + 1, cdn) : false;
-        const uint32_t t_n = t_slot0 + (uint32_t)((b ^ 1) * SLOT_COLS);
-        if (has_next) {
-          mbar_wait(smem_u32(&bars->s_full[wg][b ^ 1]), (uint32_t)(((u + 1) >> 1) & 1));   // issued a tile-time ago
-          tc_fence_after();
-          epi_step<KIND, NPOLY, true>(t_s + 48, t_lo + 24, t_n, pa, sb, pb, sa, diag, cd - 56);
-        } else {
-          epi_step<KIND, NPOLY, false>(t_s + 48, t_lo + 24, t_n, pa, sb, pb, sa, diag, cd - 56);
-        }
-        // fold O(u-1): GEMM2(wg, u-1) was issued when this warpgroup released tile u-1, a tile-time ago
+        GP_TMEM_LD8(t_s + 16, s2);
+        cov_group8<KIND, NPOLY>(s0, pa);
+        epi_step<KIND, NPOLY, 1>(t_s, t_lo, t_s + 24, pa, s1, pb, s3, s3, diag, cd - 8);       // MUFU g1, load g3, store g0
+        epi_step<KIND, NPOLY, 0>(t_s + 8, t_lo + 4, t_s, pb, s2, pa, s0, s0, diag, cd - 16);   // MUFU g2, store g1
+        epi_step<KIND, NPOLY, 0>(t_s + 16, t_lo + 8, t_s, pa, s3, pb, s0, s0, diag, cd - 24);  // MUFU g3, store g2
+        // fold this warp's 8 columns of O(u-1) before P(u) is released (GEMM2(wg, u) overwrites O): GEMM2(wg, u-1) was issued
+        // when the warpgroup released tile u-1, most of a tile-time ago
         if (u >= 1) {
           mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)((u - 1) & 1));
           tc_fence_after();
-          uint32_t o[16];
-          GP_TMEM_LD16(t_o, o);
-          tmem_wait_ld();            // also completes the S load issued in step 6
+          uint32_t o[8];
+          GP_TMEM_LD8(t_o, o);
+          tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]);
+          for (int c = 0; c < 8; ++c) acc[c] += __uint_as_float(o[c]);
         }
-        if (has_next) {
-          epi_step<KIND, NPOLY, true>(t_s + 56, t_lo + 28, t_n + 8, pb, sa, pa, sb, diagn, cdn);
-        } else {
-          // last tile: only the store of group 7 is left
+        {
           uint32_t hi[8], lo[4];
           split_group8(pb, hi, lo);
-          GP_TMEM_ST8(t_s + 56, hi);
-          GP_TMEM_ST4(t_lo + 28, lo);
+          GP_TMEM_ST8(t_s + 24, hi);
+          GP_TMEM_ST4(t_lo + 12, lo);
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[wg][b]));  // GEMM2(wg, u) may now read P and overwrite O(wg)
-        if (q == 0) GP_TR2(u, 4 + wg);
-        diag = diagn;
-        cd = cdn;
+        if (q == 0 && h == 0) GP_TR2(u, 4 + wg);
       }
       // the last tile's product is still in TMEM
       mbar_wait(smem_u32(&bars->o_full[wg]), (uint32_t)((T - 1) & 1));
       tc_fence_after();
-      uint32_t o[16];
-      GP_TMEM_LD16(t_o, o);
+      uint32_t o[8];
+      GP_TMEM_LD8(t_o, o);
       tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < TP; ++c) acc[c] += __uint_as_float(o[c]);
+      for (int c = 0; c < 8; ++c) acc[c] += __uint_as_float(o[c]);
     }
-    float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + rloc) * TP);
-#pragma unroll
-    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+    float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)split * rows_pad + rloc) * TP + h * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   tc_fence_before();
   __syncthreads();
@@ -458,7 +505,7 @@ static int smem_bytes(int KP, bool a_tmem, int* ns_out) {
   return a_bytes + ns * stage + (int)sizeof(Bars) + 64;
 }
 
-template <int KIND, int NPOLY, bool A_TMEM>
+template <int KIND, int NPOLY, bool A_TMEM, bool TRACE = false>
 static int launch_one(gp_plan* p, const int* done_flag) {
   int ns = 0;
   const int smem = smem_bytes(p->KP, A_TMEM, &ns);
@@ -466,11 +513,11 @@ static int launch_one(gp_plan* p, const int* done_flag) {
   static bool attr_done[64] = {};   // function attributes are per device
   const int dev_slot = p->device & 63;
   if (!attr_done[dev_slot]) {
-    GP_CUDA(cudaFuncSetAttribute(kmv_tc2_kernel<KIND, NPOLY, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GP_CUDA(cudaFuncSetAttribute(kmv_tc2_kernel<KIND, NPOLY, A_TMEM, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[dev_slot] = true;
   }
   dim3 grid((unsigned)(p->rows_pad / ROWS_CTA), (unsigned)p->nsplit);
-  kmv_tc2_kernel<KIND, NPOLY, A_TMEM><<<grid, THREADS, smem, p->stream>>>(
+  kmv_tc2_kernel<KIND, NPOLY, A_TMEM, TRACE><<<grid, THREADS, smem, p->stream>>>(
       p->XA.as<float>(), p->XB.as<float>(), p->Vtiles.as<float>(), p->partial.as<float>(), p->KP, ns, p->ntile_j,
       p->tiles_per_split, p->rows_pad, p->same ? 1 : 0, p->row_begin, done_flag, p->tc_trace);
   p->launches++;
@@ -482,6 +529,7 @@ template <int KIND>
 static int launch_kind(gp_plan* p, const int* done_flag) {
   const bool a_tmem = p->KP <= A_COLS_MAX;
   const int npoly = p->npoly;
+  if (KIND == GP_RBF && p->tc_trace && a_tmem && npoly == 0) return launch_one<GP_RBF, 0, true, true>(p, done_flag);   // tools/tc_trace2.py
 #define GP_V2_CASE(NP)                                                   \
   case NP:                                                               \
     return a_tmem ? launch_one<KIND, NP, true>(p, done_flag) : launch_one<KIND, NP, false>(p, done_flag);

@@ -154,9 +154,11 @@ int choose_geometry(gp_plan* p) {
   p->ntile_j = cdiv(p->n2, TILE_J);
   p->tc2 = p->backend == GP_BACKEND_TCGEN05 && p->KP <= 64 && getenv("GP_KMV_V1") == nullptr;
   {
+    // share of the ex2 evaluations on the FMA pipe (of 8): measured best at C2 / C3 shapes (profiles/NOTES_r02.md): RBF is bound by
+    // the issuer <-> epilogue hand-off, not by the MUFU, so the polynomial only adds issue slots; Matern (sqrt + ex2 per entry) gains
     const char* e = getenv("GP_NPOLY");
-    p->npoly = e ? atoi(e) : 2;
-    if (p->npoly != 0 && p->npoly != 2 && p->npoly != 4) p->npoly = 2;
+    p->npoly = e ? atoi(e) : (p->kind == GP_RBF ? 0 : 2);
+    if (p->npoly != 0 && p->npoly != 2 && p->npoly != 4) p->npoly = 0;
   }
   // column splits: pick the smallest nsplit whose unit count fills the SMs best
   int64_t nti = (p->backend == GP_BACKEND_TCGEN05) ? (p->tc2 ? p->rows_pad / (2 * TILE_I) : p->ntile_i) : cdiv(p->row_count, SIMT_TI);

@@ -40,6 +40,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// polling wait (no hardware suspend): for the MMA issuer, whose wake-up latency is on the critical path of every tile
+// (try_wait parks the thread and took 200-300 cycles to notice a completed phase; profiles/NOTES_r02.md)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_poll(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+
 // ---- named barriers (bar.sync / bar.arrive on ids 1..15; id 0 is __syncthreads) --------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
