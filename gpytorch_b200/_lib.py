@@ -66,6 +66,7 @@ PROTOTYPES = {
     "gp_plan_set_backend": (_I, [_P, _I]),
     "gp_plan_set_data": (_I, [_P, _P, _L, _L, _P, _L, _L, _I, _L, _L]),
     "gp_plan_set_hypers": (_I, [_P, _I, C.POINTER(_F), _I, _F, _F]),
+    "gp_plan_set_noise_diag": (_I, [_P, _P, _L]),
     "gp_kmv": (_I, [_P, _P, _L, _I, _P, _L, _I]),
     "gp_krows": (_I, [_P, _P, _L, _P, _L]),
     "gp_kdiag": (_I, [_P, _P]),

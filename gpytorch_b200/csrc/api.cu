@@ -164,6 +164,14 @@ extern "C" int gp_plan_set_hypers(gp_plan* p, int kind, const float* lengthscale
   return GP_OK;
 }
 
+extern "C" int gp_plan_set_noise_diag(gp_plan* p, const float* diag, int64_t n) {
+  GP_REQUIRE(p != nullptr, GP_E_STATE, "null plan");
+  GP_REQUIRE(diag == nullptr || (p->data_set && p->same && n == p->n2), GP_E_SHAPE,
+             "the noise diagonal needs one entry per row of a square operator (n=%lld)", (long long)n);
+  p->noise_diag = diag;
+  return GP_OK;
+}
+
 extern "C" int gp_kmv(gp_plan* p, const float* V, int64_t ldv, int t, float* OUT, int64_t ldo, int add_noise) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready (set_data + set_hypers)");
   GP_REQUIRE(t >= 1 && ldv >= t && ldo >= t, GP_E_SHAPE, "bad K.V shape t=%d ldv=%lld ldo=%lld", t, (long long)ldv, (long long)ldo);

@@ -120,6 +120,7 @@ struct gp_plan {
   int kind = GP_RBF;
   std::vector<float> ls;
   float outputscale = 1.f, noise = 0.f;
+  const float* noise_diag = nullptr;  // optional per-row diagonal D [n2] (FixedNoiseGaussianLikelihood); replaces the scalar noise
   // derived geometry
   int DP = 0;      // padded feature width of the SIMT arrays
   int KP = 0;      // padded augmented width (3d+4 -> multiple of 8) of the tcgen05 tiles
@@ -153,7 +154,7 @@ int kmv_tc_launch(gp_plan* p, const int* done_flag);
 int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t, int add_noise);
 int choose_geometry(gp_plan* p);
 
-inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers -----------------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -114,8 +114,8 @@ int kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
 
 // OUT[r, c] = os * sum_s partial[s][r][c] + noise * V16[row_begin + r][c]
 __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int nsplit, int64_t rows, int64_t rows_pad,
-                                       float os, float noise_add, const float* __restrict__ V16, int64_t row_begin,
-                                       float* __restrict__ OUT, int64_t ldo, int t, const int* __restrict__ xbad) {
+                                       float os, float noise_add, const float* __restrict__ dvec, const float* __restrict__ V16,
+                                       int64_t row_begin, float* __restrict__ OUT, int64_t ldo, int t, const int* __restrict__ xbad) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * TP) return;
   int64_t r = idx / TP;
@@ -124,7 +124,8 @@ __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int ns
   float s = 0.f;
   for (int sp = 0; sp < nsplit; ++sp) s += partial[((int64_t)sp * rows_pad + r) * TP + c];
   float o = os * s;
-  if (noise_add != 0.f) o = fmaf(noise_add, V16[(row_begin + r) * TP + c], o);
+  if (dvec) o = fmaf(dvec[row_begin + r], V16[(row_begin + r) * TP + c], o);
+  else if (noise_add != 0.f) o = fmaf(noise_add, V16[(row_begin + r) * TP + c], o);
   if (*xbad) o = __int_as_float(0x7fc00000);
   OUT[r * ldo + c] = o;
 }
@@ -133,8 +134,9 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
   int64_t rows_pad = p->rows_pad;
   int64_t tot = p->row_count * TP;
   float na = (add_noise && p->same) ? p->noise : 0.f;
+  const float* dv = (add_noise && p->same) ? p->noise_diag : nullptr;
   kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count,
-                                                                          rows_pad, p->outputscale, na, V16, p->row_begin,
+                                                                          rows_pad, p->outputscale, na, dv, V16, p->row_begin,
                                                                           OUT, ldo, t, p->xbad);
   p->launches++;
   GP_CUDA(cudaGetLastError());

@@ -321,38 +321,83 @@ __global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm,
 }
 
 // ---- preconditioner factor ---------------------------------------------------------------------
-// Gpart[z][a][b] = sum_{j in slice z} L[a][j] L[b][j]   (fp64)
-__global__ void gram_kernel(const float* __restrict__ Lt, int k, int64_t n, int64_t jslice, double* __restrict__ Gpart) {
-  __shared__ double A[16][65];   // staged as fp64: the (exact) conversion happens once per element, not once per FMA
-  __shared__ double B[16][65];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+// Gpart[z][a][b] = sum_{j in slice z} L[a][j] L[b][j] s_j     (s_j = 1, or 1 / d_j for a per-row noise diagonal)
+// 64 x 64 output tiles, 4 x 4 register tiles per thread.  Products and sums run in fp32 over chunks of 64 columns (<= 64 terms of
+// magnitude <= outputscale: absolute error ~1e-6 per chunk), every chunk is then added to fp64 accumulators: the error of G
+// stays orders of magnitude below the noise floor it is compared with in  log det P = log det(L^T L + sigma^2 I) + ...  (an
+// error E in G shifts log det P by ~tr(E) / sigma^2), at a fraction of the cost of the all-fp64 product of round 1 (0.38 ms at C2).
+constexpr int GT = 64;
+__global__ void __launch_bounds__(256)
+gram_kernel(const float* __restrict__ Lt, int k, int64_t n, int64_t jslice, const float* __restrict__ dvec, double* __restrict__ Gpart) {
+  if (blockIdx.x > blockIdx.y) return;   // lower triangle of tiles only; the mirror image is written below
+  __shared__ __align__(16) float As[32][GT + 4];   // [column][row of L^T = index a]
+  __shared__ __align__(16) float Bs[32][GT + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int a0 = blockIdx.y * GT, b0 = blockIdx.x * GT;
   const int64_t j_begin = (int64_t)blockIdx.z * jslice, j_end = min(n, j_begin + jslice);
-  double acc = 0.0;
+  double acc64[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc64[i][j] = 0.0;
   for (int64_t j0 = j_begin; j0 < j_end; j0 += 64) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int r = e >> 6, cc = e & 63;
-      int64_t j = j0 + cc;
-      A[r][cc] = (a0 + r < k && j < j_end) ? (double)Lt[(int64_t)(a0 + r) * n + j] : 0.0;
-      B[r][cc] = (b0 + r < k && j < j_end) ? (double)Lt[(int64_t)(b0 + r) * n + j] : 0.0;
-    }
-    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int hf = 0; hf < 2; ++hf) {
+      const int64_t jb = j0 + hf * 32;
+      __syncthreads();
+      for (int e = tid; e < GT * 32; e += 256) {
+        const int r = e >> 5, cc = e & 31;
+        const int64_t j = jb + cc;
+        const bool ok = j < j_end;
+        const float sc = (ok && dvec) ? 1.f / dvec[j] : 1.f;
+        As[cc][r] = (ok && a0 + r < k) ? Lt[(int64_t)(a0 + r) * n + j] * sc : 0.f;
+        Bs[cc][r] = (ok && b0 + r < k) ? Lt[(int64_t)(b0 + r) * n + j] : 0.f;
+      }
+      __syncthreads();
 #pragma unroll 8
-    for (int cc = 0; cc < 64; ++cc) acc = fma(A[ty][cc], B[tx][cc], acc);
+      for (int cc = 0; cc < 32; ++cc) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[cc][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[cc][tx * 4]);
+        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc64[i][j] += (double)acc[i][j];
   }
-  if (a0 + ty < k && b0 + tx < k) Gpart[((int64_t)blockIdx.z * k + a0 + ty) * k + b0 + tx] = acc;
+  double* G = Gpart + (int64_t)blockIdx.z * k * k;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + ty * 4 + i, b = b0 + tx * 4 + j;
+      if (a < k && b < k) {
+        G[(int64_t)a * k + b] = acc64[i][j];
+        if (blockIdx.x != blockIdx.y) G[(int64_t)b * k + a] = acc64[i][j];
+      }
+    }
 }
 
 // single CTA: G = sum_z Gpart + noise I ; in-place lower Cholesky C ; logdet
-__global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int k, double noise, int64_t n,
+// diag_add = sigma^2 and logdet_tail = (n - k) log sigma^2 for the constant diagonal; 1 and sum_j log d_j for a per-row diagonal
+// (then G = L^T D^-1 L and log det P = log det(I + L^T D^-1 L) + sum log d)
+__global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int k, double diag_add, const double* __restrict__ logdet_tail,
                                   double* __restrict__ C, double* __restrict__ logdet_out, int* __restrict__ fail) {
   extern __shared__ double G[];  // [k][k]
   const int tid = threadIdx.x;
   for (int e = tid; e < k * k; e += blockDim.x) {
     double s = 0.0;
     for (int z = 0; z < nz; ++z) s += Gpart[(int64_t)z * k * k + e];
-    if (e / k == e % k) s += noise;
+    if (e / k == e % k) s += diag_add;
     G[e] = s;
   }
   __syncthreads();
@@ -378,57 +423,63 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
   if (tid == 0) {
     double ld = 0.0;
     for (int j = 0; j < k; ++j) ld += log(G[j * k + j]);
-    *logdet_out = 2.0 * ld + (double)(n - k) * log(noise);
+    *logdet_out = 2.0 * ld + *logdet_tail;
   }
 }
 
-// Cinv = C^{-1} (lower triangular, fp64): one thread per column, forward substitution against C in shared memory
-__global__ void cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
-  extern __shared__ double Is[];  // [k][k] C^{-1}, built column by column in shared memory (C itself: broadcast loads, L1)
-  const int j = threadIdx.x;
-  if (j < k) {
-    for (int i = 0; i < k; ++i) {
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int b = j; b < i; ++b) s -= __ldg(C + i * k + b) * Is[b * k + j];
-      Is[i * k + j] = (i < j) ? 0.0 : s / __ldg(C + i * k + i);
-    }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cinv[e] = Is[e];
-}
-
-constexpr int WS_BLOCKS = 4;
-// W[r][a] = sum_{b<=a} Cinv[a][b] L[b][r]   (W = L C^{-T}); 32 rows x 4 interleaved a-groups per pass, fp64 accumulate
-__global__ void __launch_bounds__(128)
+// W[r][:] = C^{-1} (s_r L[:, r])  (W = L C^{-T}, rows scaled by s_r = 1 / d_r for a per-row noise diagonal): one thread per row runs
+// the forward substitution against C (fp64, shared memory, broadcast reads) with its partial results w_b in shared memory (fp32,
+// [b][thread]: conflict free); four independent partial sums break the dependent FMA chain.  Replaces the explicit inverse
+// C^{-1} + dense [k x k] . [k x n] product of round 1 (0.16 + 0.19 ms at C2).
+constexpr int WS_THREADS = 128;
+__global__ void __launch_bounds__(WS_THREADS)
 wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
-              const double* __restrict__ Cinv, float* __restrict__ W) {
+              const double* __restrict__ C, const float* __restrict__ dvec, float* __restrict__ W) {
   extern __shared__ double shw[];
-  double* Ci = shw;                        // [k][k]
-  double* Ls = shw + (size_t)k * k;        // [k][32], fp64 copy of the L rows (exact conversion, once per element)
-  for (int e = threadIdx.x; e < k * k; e += 128) Ci[e] = Cinv[e];
-  const int rl = threadIdx.x & 31, ag = threadIdx.x >> 5;
-  for (int blk = 0; blk < WS_BLOCKS; ++blk) {          // C^{-1} (80 KB at k = 100) is loaded once per WS_BLOCKS * 32 rows
-    const int64_t r0 = ((int64_t)blockIdx.x * WS_BLOCKS + blk) * 32;
-    if (r0 >= n_local) break;
-    __syncthreads();
-    for (int e = threadIdx.x; e < k * 32; e += 128) {
-      int b = e >> 5, rr = e & 31;
-      Ls[e] = (r0 + rr < n_local) ? (double)Lt[(int64_t)b * n_total + row_begin + r0 + rr] : 0.0;
-    }
-    __syncthreads();
-    const int64_t r = r0 + rl;
-    for (int a = ag; a < k; a += 4) {
-      double s = 0.0;
-      for (int b = 0; b <= a; ++b) s = fma(Ci[a * k + b], Ls[b * 32 + rl], s);
-      if (r < n_local) W[r * k + a] = (float)s;
+  double* Cs = shw;                                             // [k][k] lower triangle of C
+  float* wcol = reinterpret_cast<float*>(shw + (size_t)k * k);  // [k][WS_THREADS]
+  for (int e = threadIdx.x; e < k * k; e += WS_THREADS) Cs[e] = C[e];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  for (int64_t r = (int64_t)blockIdx.x * WS_THREADS + tid; r < n_local; r += (int64_t)gridDim.x * WS_THREADS) {
+    const int64_t gr = row_begin + r;
+    const double sc = dvec ? 1.0 / (double)dvec[gr] : 1.0;
+    for (int a = 0; a < k; ++a) {
+      double s0 = sc * (double)Lt[(int64_t)a * n_total + gr], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double* ca = Cs + (size_t)a * k;
+      int b = 0;
+      for (; b + 4 <= a; b += 4) {
+        s0 = fma(-ca[b], (double)wcol[b * WS_THREADS + tid], s0);
+        s1 = fma(-ca[b + 1], (double)wcol[(b + 1) * WS_THREADS + tid], s1);
+        s2 = fma(-ca[b + 2], (double)wcol[(b + 2) * WS_THREADS + tid], s2);
+        s3 = fma(-ca[b + 3], (double)wcol[(b + 3) * WS_THREADS + tid], s3);
+      }
+      for (; b < a; ++b) s0 = fma(-ca[b], (double)wcol[b * WS_THREADS + tid], s0);
+      const float w = (float)(((s0 + s1) + (s2 + s3)) / ca[a]);
+      wcol[a * WS_THREADS + tid] = w;
+      W[r * k + a] = w;
     }
   }
+}
+
+// sum_j log d_j (fp64, one CTA; the per-row-noise tail of log det P)
+__global__ void logsum_kernel(const float* __restrict__ d, int64_t n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += 256) s += log((double)d[j]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
 }
 
 // Z[r][c] = sum_a L[a][r] eps1[a][c] + sigma eps2[r][c]
 __global__ void probes_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
                               const float* __restrict__ eps1, const float* __restrict__ eps2, int tp, float sigma,
-                              float* __restrict__ Z) {
+                              const float* __restrict__ dvec, float* __restrict__ Z) {
   extern __shared__ float e1[];  // [k][tp]
   for (int e = threadIdx.x; e < k * tp; e += blockDim.x) e1[e] = eps1[e];
   __syncthreads();
@@ -436,7 +487,7 @@ __global__ void probes_kernel(const float* __restrict__ Lt, int k, int64_t n_tot
   if (idx >= n_local * tp) return;
   int64_t r = idx / tp;
   int c = (int)(idx % tp);
-  float s = sigma * eps2[r * tp + c];
+  float s = (dvec ? sqrtf(dvec[row_begin + r]) : sigma) * eps2[r * tp + c];   // z = L eps1 + D^1/2 eps2
   for (int a = 0; a < k; ++a) s = fmaf(Lt[(int64_t)a * n_total + row_begin + r], e1[a * tp + c], s);
   Z[r * tp + c] = s;
 }
@@ -522,34 +573,47 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
 extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, double* logdet_out) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(k >= 1 && k <= 128, GP_E_SHAPE, "preconditioner rank %d not in [1,128]", k);
-  GP_REQUIRE(p->noise > 0.f, GP_E_SHAPE, "preconditioner needs noise > 0");
+  const float* dvec = p->noise_diag;
+  GP_REQUIRE(dvec != nullptr || p->noise > 0.f, GP_E_SHAPE, "preconditioner needs noise > 0");
   cudaStream_t st = p->stream;
   const int64_t n = p->n2;
-  const int nz = (int)std::min<int64_t>(16, std::max<int64_t>(1, n / 4096));
+  const int ntile = (int)cdiv(k, GT);
+  const int nz = (int)std::min<int64_t>(64, std::max<int64_t>(1, std::min<int64_t>(n / 1024, (2 * p->n_sm) / (ntile * (ntile + 1) / 2))));
   const int64_t jslice = cdiv(cdiv(n, nz), 64) * 64;
   GP_CHECK(p->gram.ensure(sizeof(double) * (size_t)nz * k * k));
-  GP_CHECK(p->cholC.ensure(sizeof(double) * (size_t)2 * k * k + 64));
+  GP_CHECK(p->cholC.ensure(sizeof(double) * ((size_t)k * k + 4) + 64));
   double* C = p->cholC.as<double>();
-  double* Cinv = C + (size_t)k * k;
-  double* d_logdet = Cinv + (size_t)k * k;
-  int* d_fail = reinterpret_cast<int*>(d_logdet + 1);
+  double* d_logdet = C + (size_t)k * k;
+  double* d_tail = d_logdet + 1;
+  int* d_fail = reinterpret_cast<int*>(d_tail + 1);
   GP_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
-  dim3 gg((unsigned)cdiv(k, 16), (unsigned)cdiv(k, 16), (unsigned)nz);
-  gram_kernel<<<gg, 256, 0, st>>>(Lt, k, n, jslice, p->gram.as<double>());
-  size_t shc = sizeof(double) * (size_t)k * k;
-  GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // k <= 128: 128 KB
-  GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));         // 128 KB + 32 KB
-  chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, (double)p->noise, n, C, d_logdet, d_fail);
-  GP_CUDA(cudaFuncSetAttribute(cinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  cinv_kernel<<<1, 128, shc, st>>>(C, k, Cinv);
-  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32 * WS_BLOCKS), 128, shc + sizeof(double) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin, p->row_count, Cinv, W);
-  p->launches += 4;
+  dim3 gg((unsigned)ntile, (unsigned)ntile, (unsigned)nz);
+  gram_kernel<<<gg, 256, 0, st>>>(Lt, k, n, jslice, dvec, p->gram.as<double>());
+  if (dvec) {
+    logsum_kernel<<<1, 256, 0, st>>>(dvec, n, d_tail);
+    p->launches++;
+  } else {
+    const double tail = (double)(n - k) * log((double)p->noise);
+    GP_CUDA(cudaMemcpyAsync(d_tail, &tail, sizeof(double), cudaMemcpyHostToDevice, st));   // pageable source: copied before return
+  }
+  const size_t shc = sizeof(double) * (size_t)k * k;
+  const size_t shw = shc + sizeof(float) * (size_t)k * WS_THREADS;
+  static bool attr_done[64] = {};
+  if (!attr_done[p->device & 63]) {
+    GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // k <= 128: 128 KB
+    GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       // 128 KB + 64 KB
+    attr_done[p->device & 63] = true;
+  }
+  chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, dvec ? 1.0 : (double)p->noise, d_tail, C, d_logdet, d_fail);
+  wsolve_kernel<<<(unsigned)std::min<int64_t>(cdiv(p->row_count, WS_THREADS), 4 * p->n_sm), WS_THREADS, shw, st>>>(
+      Lt, k, n, p->row_begin, p->row_count, C, dvec, W);
+  p->launches += 3;
   GP_CUDA(cudaGetLastError());
   double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(p->pinned) + 3072);
-  GP_CUDA(cudaMemcpyAsync(h, d_logdet, sizeof(double) + sizeof(int), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(cudaMemcpyAsync(h, d_logdet, sizeof(double) * 2 + sizeof(int), cudaMemcpyDeviceToHost, st));
   GP_CUDA(cudaStreamSynchronize(st));
   if (logdet_out) *logdet_out = h[0];
-  int fail = *reinterpret_cast<int*>(h + 1);
+  int fail = *reinterpret_cast<int*>(h + 2);
   GP_REQUIRE(!fail, GP_W_PIVCHOL_NAN, "preconditioner Gram matrix is not positive definite");
   return GP_OK;
 }
@@ -559,7 +623,7 @@ extern "C" int gp_precond_probes(gp_plan* p, const float* Lt, int k, const float
   GP_REQUIRE(k >= 1 && tp >= 1 && (size_t)k * tp * 4 <= 40 * 1024, GP_E_SHAPE, "bad probe shape k=%d tp=%d", k, tp);
   int64_t tot = p->row_count * tp;
   probes_kernel<<<(unsigned)cdiv(tot, 256), 256, sizeof(float) * k * tp, p->stream>>>(Lt, k, p->n2, p->row_begin, p->row_count,
-                                                                                  eps1, eps2, tp, sqrtf(p->noise), Z);
+                                                                                  eps1, eps2, tp, sqrtf(p->noise), p->noise_diag, Z);
   p->launches++;
   GP_CUDA(cudaGetLastError());
   return GP_OK;

@@ -94,6 +94,17 @@ class Plan:
             check(self.lib.gp_plan_set_hypers(self._h, KIND[kind], arr, len(ls), float(outputscale), float(noise)))
         return self
 
+    def set_noise_diag(self, diag: torch.Tensor | None):
+        """Per-row noise variances (FixedNoiseGaussianLikelihood): K_hat = K + diag(d).  None restores the scalar noise."""
+        if diag is None:
+            self._noise_diag = None
+            check(self.lib.gp_plan_set_noise_diag(self._h, _ptr(None), 0))
+            return self
+        _require_cuda_f32(diag, "noise diagonal")
+        self._noise_diag = diag.contiguous()      # keep it alive: the engine holds the raw pointer
+        check(self.lib.gp_plan_set_noise_diag(self._h, _ptr(self._noise_diag), self._noise_diag.numel()))
+        return self
+
     def info(self):
         b, s, k, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(self.lib.gp_plan_info(self._h, C.byref(b), C.byref(s), C.byref(k), C.byref(m)))

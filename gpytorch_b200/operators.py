@@ -253,9 +253,9 @@ class KernelLinearOperator:
         return KernelLinearOperator(x1, x2, self.kind, self.lengthscale, self.outputscale)
 
     def __add__(self, other):
-        if isinstance(other, ConstantDiagLinearOperator):
+        if isinstance(other, (ConstantDiagLinearOperator, DiagLinearOperator)):
             return AddedDiagLinearOperator(self, other)
-        raise NotImplementedError("KernelLinearOperator only adds a ConstantDiagLinearOperator")
+        raise NotImplementedError("KernelLinearOperator only adds a (Constant)DiagLinearOperator")
 
     def add_jitter(self, jitter_val=1e-3):
         return AddedDiagLinearOperator(self, ConstantDiagLinearOperator(torch.tensor(jitter_val, device=self.device), self.shape[0]))
@@ -298,18 +298,28 @@ class _KernelMatmul(torch.autograd.Function):
 
 
 class AddedDiagLinearOperator:
-    """K + sigma^2 I with the BBMM solves (linear_operator AddedDiagLinearOperator, constant-diagonal case)."""
+    """K + D with the BBMM solves (linear_operator AddedDiagLinearOperator): D = sigma^2 I (constant-diagonal branch, Appendix
+    A.4) or a per-row diagonal (FixedNoiseGaussianLikelihood; the non-constant-diagonal branch of the preconditioner)."""
 
-    def __init__(self, kernel_op: KernelLinearOperator, diag: ConstantDiagLinearOperator):
+    def __init__(self, kernel_op: KernelLinearOperator, diag):
         if kernel_op.shape[0] != kernel_op.shape[1]:
             raise RuntimeError("AddedDiagLinearOperator needs a square operator")
         self.kernel_op = kernel_op
         self.diag = diag
+        self.per_row = isinstance(diag, DiagLinearOperator)
         self._precond_cache = None
 
     @property
     def noise(self) -> torch.Tensor:
-        return self.diag.diag_value.reshape(())
+        """sigma^2 (0-d) for the constant diagonal, the vector d [n] for a per-row diagonal."""
+        return self.diag.diag_vec if self.per_row else self.diag.diag_value.reshape(())
+
+    @property
+    def _noise_param(self) -> torch.Tensor:
+        return self.diag.diag_vec if self.per_row else self.diag.diag_value
+
+    def _noise_col(self):
+        return self.diag.diag_vec.unsqueeze(-1) if self.per_row else self.noise
 
     @property
     def shape(self):
@@ -334,12 +344,23 @@ class AddedDiagLinearOperator:
         return self
 
     def _plan(self) -> Plan:
+        if self.per_row:
+            p = self.kernel_op.plan(0.0)
+            d = self.diag.diag_vec.detach().float().contiguous()
+            if getattr(p, "_noise_diag", None) is None or p._noise_diag.data_ptr() != d.data_ptr() or p._noise_diag_version != d._version:
+                p.set_noise_diag(d)
+                p._noise_diag_version = d._version
+            self.kernel_op._last_noise = 0.0
+            return p
         p = self.kernel_op.plan(self.diag.diag_value)
+        if getattr(p, "_noise_diag", None) is not None:   # a cached plan last used with a per-row diagonal
+            p.set_noise_diag(None)
         self.kernel_op._last_noise = p.noise
         return p
 
     def matmul(self, rhs):
-        return self.kernel_op.matmul(rhs) + self.noise * rhs
+        d = self._noise_col() if (self.per_row and rhs.dim() > 1) else self.noise
+        return self.kernel_op.matmul(rhs) + d * rhs
 
     __matmul__ = matmul
     _matmul = matmul
@@ -362,10 +383,10 @@ class AddedDiagLinearOperator:
 
     @property
     def requires_grad(self):
-        return bool(self.kernel_op.requires_grad or self.diag.diag_value.requires_grad)
+        return bool(self.kernel_op.requires_grad or self._noise_param.requires_grad)
 
     def representation(self):
-        return self.kernel_op.representation() + (self.diag.diag_value,)
+        return self.kernel_op.representation() + (self._noise_param,)
 
     def transpose(self, dim1, dim2):
         return self          # K + sigma^2 I is symmetric
@@ -380,12 +401,13 @@ class AddedDiagLinearOperator:
         return self
 
     def detach(self):
-        return AddedDiagLinearOperator(self.kernel_op.detach(), ConstantDiagLinearOperator(self.diag.diag_value.detach(), self.shape[0]))
+        d = DiagLinearOperator(self.diag.diag_vec.detach()) if self.per_row else ConstantDiagLinearOperator(self.diag.diag_value.detach(), self.shape[0])
+        return AddedDiagLinearOperator(self.kernel_op.detach(), d)
 
     def __add__(self, other):
-        if isinstance(other, ConstantDiagLinearOperator):   # (K + a I) + b I
-            return AddedDiagLinearOperator(self.kernel_op, ConstantDiagLinearOperator(self.noise + other.diag_value.reshape(()), self.shape[0]))
-        raise NotImplementedError("AddedDiagLinearOperator only adds a ConstantDiagLinearOperator")
+        if isinstance(other, (ConstantDiagLinearOperator, DiagLinearOperator)):   # (K + D1) + D2
+            return AddedDiagLinearOperator(self.kernel_op, self.diag + other)
+        raise NotImplementedError("AddedDiagLinearOperator only adds a (Constant)DiagLinearOperator")
 
     def logdet(self):
         return self.inv_quad_logdet(None, logdet=True)[1]
@@ -402,7 +424,8 @@ class AddedDiagLinearOperator:
     _diagonal = diagonal
 
     def add_jitter(self, jitter_val=1e-3):
-        return AddedDiagLinearOperator(self.kernel_op, ConstantDiagLinearOperator(self.noise + jitter_val, self.shape[0]))
+        jit = ConstantDiagLinearOperator(torch.as_tensor(jitter_val, device=self.device, dtype=self.dtype), self.shape[0])
+        return AddedDiagLinearOperator(self.kernel_op, self.diag + jit)
 
     # -- preconditioner (AddedDiagLinearOperator._preconditioner, Appendix A.4) --
     def _preconditioner(self):
@@ -438,7 +461,7 @@ class AddedDiagLinearOperator:
 
     def solve(self, rhs, lhs=None):
         """K_hat^{-1} rhs by preconditioned CG (LinearOperator.solve -> linear_cg, n_tridiag = 0)."""
-        out = _Solve.apply(self, rhs, self.kernel_op.lengthscale, self.kernel_op.outputscale, self.diag.diag_value)
+        out = _Solve.apply(self, rhs, self.kernel_op.lengthscale, self.kernel_op.outputscale, self._noise_param)
         return out if lhs is None else lhs @ out
 
     def inv_quad_logdet(self, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True):
@@ -451,7 +474,7 @@ class AddedDiagLinearOperator:
         if rhs is not None and rhs.dim() == 1:
             rhs = rhs.unsqueeze(-1)
         iq, ld = _InvQuadLogdet.apply(self, rhs, bool(logdet), self.kernel_op.lengthscale, self.kernel_op.outputscale,
-                                      self.diag.diag_value)
+                                      self._noise_param)
         if rhs is None:
             iq = torch.empty(0, device=self.device)
         elif reduce_inv_quad:
@@ -526,7 +549,9 @@ class _Solve(torch.autograd.Function):
             dls, dos = op.kernel_op._bilinear_derivative(-gsol, sol)
             gl = dls.reshape(op.kernel_op.lengthscale.shape) if ctx.needs_input_grad[2] else None
             go = dos.reshape(op.kernel_op.outputscale.shape) if ctx.needs_input_grad[3] else None
-            gn = (-(gsol * sol).sum()).reshape(op.diag.diag_value.shape) if ctx.needs_input_grad[4] else None
+            gn = None
+            if ctx.needs_input_grad[4]:
+                gn = (-(gsol * sol).sum(-1)) if op.per_row else (-(gsol * sol).sum()).reshape(op.diag.diag_value.shape)
         return None, grad_rhs, gl, go, gn
 
 
@@ -603,7 +628,10 @@ class _InvQuadLogdet(torch.autograd.Function):
                 pv_solves = solves[:, :tp] * coef * norms * grad_ld   # (1/tp) K^-1 z_i
                 pz = probes
                 if w.numel():
-                    pz = (probes - w @ (w.t() @ probes)) / op.noise.detach()  # P^-1 z_i
+                    if op.per_row:   # P^-1 z = z / d - W (W^T z), W pre-scaled by D^-1
+                        pz = probes / op.diag.diag_vec.detach().unsqueeze(-1) - w @ (w.t() @ probes)
+                    else:
+                        pz = (probes - w @ (w.t() @ probes)) / op.noise.detach()  # P^-1 z_i
                 left_cols.append(pv_solves); right_cols.append(pz)
             if ctx.has_rhs:
                 iq_solves = solves[:, tp:]
@@ -620,5 +648,5 @@ class _InvQuadLogdet(torch.autograd.Function):
             if ctx.needs_input_grad[4]:
                 go = dos.reshape(op.kernel_op.outputscale.shape)
             if ctx.needs_input_grad[5]:
-                gn = (left * right).sum().reshape(op.diag.diag_value.shape)
+                gn = (left * right).sum(-1) if op.per_row else (left * right).sum().reshape(op.diag.diag_value.shape)
         return None, grad_rhs, None, gl, go, gn

@@ -76,6 +76,11 @@ int gp_plan_set_data(gp_plan* plan, const float* X1, int64_t n1, int64_t ld1,
 int gp_plan_set_hypers(gp_plan* plan, int kind, const float* lengthscale, int n_ls,
                        float outputscale, float noise);
 
+/* Per-row noise diagonal D (FixedNoiseGaussianLikelihood, likelihoods/gaussian_likelihood.py:245-363; FixedGaussianNoise,
+ * noise_models.py:150-190): K_hat = K + diag(d).  `diag` is a device pointer to n2 floats (caller-owned, must outlive the plan's
+ * use of it) that replaces the scalar noise in every product / solve / preconditioner / probe; NULL restores the scalar. */
+int gp_plan_set_noise_diag(gp_plan* plan, const float* diag, int64_t n);
+
 /* ---- kernel seam (LazyEvaluatedKernelTensor, lazy/lazy_evaluated_kernel_tensor.py) --- */
 
 /* OUT[n1_local, t] = K(X1,X2) V [+ noise * V when add_noise and X2 == X1].

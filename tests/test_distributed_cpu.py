@@ -1,5 +1,6 @@
 """world_size-2 gloo test (CPU) of the row-sharded mBCG message pattern used by csrc/cg.cu + csrc/comm.cu:
-per iteration one all-gather of the owned direction block and all-reduces of the packed dot products.
+per iteration one all-gather of the owned direction block and two all-reduces of the packed dot products
+(message 1 = [p.V | W^T V], message 2 = [r.r | z.r]; the preconditioner's W^T R rides on a recurrence).
 The sharded run must reproduce the unsharded oracle."""
 import os
 import socket
@@ -48,18 +49,33 @@ def _sharded_cg(rank, world, port, n, d, q):
         return t
 
     rhs = rhs_full[b : b + c].clone()
-    # minimal re-statement of the iteration with explicit collectives (mirrors cg.cu's message schedule)
+    # the preconditioner: pivoted Cholesky + QR factor (replicated), this rank's rows of Q
+    A_full = ok.kernel_matrix("rbf", x, x, 0.25, 1.0, True)
+    L, piv = ol.pivoted_cholesky(torch.ones(n, dtype=torch.float64), lambda i: A_full[i], 10)
+    pre = ol.build_preconditioner(L, 1.0, piv)
+    W = pre.Q[b : b + c]
+    # minimal re-statement of the iteration with explicit collectives: cg.cu's message schedule.  Per iteration ONE all-gather
+    # (inside matmul_local) and TWO all-reduces: message 1 = [p.V | W^T V], message 2 = [r.r | z.r]; W^T R is carried by the
+    # recurrence w <- w - alpha o (W^T V) instead of a third reduction
     eps = 1e-10
     nrm = allreduce_((rhs**2).sum(-2, keepdim=True)).sqrt()
     rhs = rhs / nrm
-    R = rhs.clone(); U = torch.zeros_like(R); Z = R.clone(); P = Z.clone()
-    gamma = allreduce_((Z * R).sum(-2, keepdim=True))
+    R = rhs.clone(); U = torch.zeros_like(R)
+    w = allreduce_(W.t() @ R)                                   # start-up pass: W^T R_0
+    Z = (R - W @ w) / 1.0
+    msg2 = allreduce_(torch.cat([(R * R).sum(-2, keepdim=True), (Z * R).sum(-2, keepdim=True)], -1))
+    gamma = msg2[:, 5:]
+    P = Z.clone()
     for k in range(8):
         V = matmul_local(P)
-        pv = allreduce_((P * V).sum(-2, keepdim=True))
+        msg1 = allreduce_(torch.cat([(P * V).sum(-2, keepdim=True), W.t() @ V], 0))   # [1 + k_rank, t]
+        pv, wtv = msg1[:1], msg1[1:]
         alpha = torch.where(pv < eps, torch.zeros_like(pv), gamma / pv)
-        U += alpha * P; R -= alpha * V; Z = R.clone()
-        gnew = allreduce_((Z * R).sum(-2, keepdim=True))
+        U += alpha * P; R -= alpha * V
+        w = w - alpha * wtv
+        Z = (R - W @ w) / 1.0
+        msg2 = allreduce_(torch.cat([(R * R).sum(-2, keepdim=True), (Z * R).sum(-2, keepdim=True)], -1))
+        gnew = msg2[:, 5:]
         beta = torch.where(gamma < eps, torch.zeros_like(gamma), gnew / gamma)
         P = Z + beta * P; gamma = gnew
     sol_local = U * nrm
@@ -70,7 +86,7 @@ def _sharded_cg(rank, world, port, n, d, q):
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")  # fixed 8 iterations on both sides: "not converged" is expected
-            ref = ol.linear_cg(lambda v: A @ v, rhs_full, tolerance=1e-30, max_iter=8, max_tridiag_iter=8)
+            ref = ol.linear_cg(lambda v: A @ v, rhs_full, tolerance=1e-30, max_iter=8, max_tridiag_iter=8, preconditioner=pre.apply)
         q.put(((torch.cat(parts, 0) - ref).norm() / ref.norm()).item())
     dist.destroy_process_group()
 

@@ -266,3 +266,76 @@ def test_prediction_respects_active_dims(cuda_dev):
     var_ref = (Kss - Ks @ torch.linalg.solve(K, Ks.t())).diagonal()
     assert (pred.mean.double().cpu() - mean_ref).abs().max() < 2e-3
     assert (pred.variance.double().cpu() - var_ref).abs().max() < 2e-3
+
+
+def test_fixed_noise_likelihood_per_row_diagonal(Plan, cuda_dev):
+    """FixedNoiseGaussianLikelihood (likelihoods/gaussian_likelihood.py:245-363): K_hat = K + diag(d) through the device path --
+    products, the non-constant-diagonal preconditioner (log det P, P^-1, N(0, P) probes), mBCG and the MLL -- against the oracle's
+    per-row branch and dense Cholesky; then the same through the public API with a learned additional noise."""
+    n, d, kind, ls, rank = 3000, 5, "rbf", 0.8, 40
+    x, y = om.synthetic_problem(n, d, 4, torch.float32)
+    g = torch.Generator().manual_seed(3)
+    dvec = 0.02 + 0.3 * torch.rand(n, generator=g)                       # heteroscedastic variances in [0.02, 0.32]
+    K = ok.kernel_matrix(kind, x.double(), x.double(), ls, 1.3, True)
+    p = Plan(x.to(cuda_dev)).set_hypers(kind, ls, 1.3, 0.0).set_noise_diag(dvec.to(cuda_dev))
+    v = torch.randn(n, 6, generator=g)
+    assert rel(p.kmv(v.to(cuda_dev), add_noise=True), K @ v.double() + dvec.double().unsqueeze(-1) * v.double()) < 5e-6
+    # preconditioner of the non-constant diagonal: log det P and P^-1 against the oracle's QR form
+    lt, piv, st = p.pivoted_cholesky(rank, 1e-3)
+    L, piv_o = ol.pivoted_cholesky(torch.full((n,), 1.3, dtype=torch.float64), lambda i: K[i], rank)
+    assert torch.equal(piv.cpu(), piv_o)
+    pre = ol.build_preconditioner(L, dvec.double(), piv_o)
+    w, logdet_p, st2 = p.precond_build(lt)
+    assert st2 == 0 and logdet_p == pytest.approx(pre.logdet, rel=1e-6)
+    wd = w.double().cpu()
+    r = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    assert rel(r / dvec.double().unsqueeze(-1) - wd @ (wd.t() @ r), pre.apply(r)) < 1e-4
+    # the MLL with identical probes
+    pn = om.make_probe_noise(n, rank, 10, 7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o64 = om.mll_bbmm(kind, x.double(), y.double(), 0.0, ls, 1.3, dvec.double(), tuple(a.double() for a in pn), precond_size=rank, K=K)
+        o32 = om.mll_bbmm(kind, x, y, 0.0, ls, 1.3, dvec, pn, precond_size=rank)
+    res, sol = p.mll(y.to(cuda_dev), pn[0].to(cuda_dev), pn[1].to(cuda_dev), pn[2].to(cuda_dev), 10, rank, 2000, want_solve=True)
+    assert res.cg_iters == o64.iters
+    assert abs(res.inv_quad - o64.inv_quad) <= max(1e-4 * abs(o64.inv_quad), 3 * abs(o32.inv_quad - o64.inv_quad))
+    assert abs(res.logdet - o64.logdet) <= max(1e-4 * abs(o64.logdet), 3 * abs(o32.logdet - o64.logdet))
+    dense = om.mll_cholesky(kind, x.double(), y.double(), 0.0, ls, 1.3, dvec.double())
+    assert abs(res.mll - dense.mll) < 0.02 * abs(dense.mll) + 1e-3
+    p.close()
+    # public API: FixedNoiseGaussianLikelihood + learned second noise, gradient of the learned noise vs dense autograd
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    lik = gp.likelihoods.FixedNoiseGaussianLikelihood(noise=dvec.to(cuda_dev), learn_additional_noise=True).to(cuda_dev)
+    lik.second_noise = 0.05
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(x.to(cuda_dev), y.to(cuda_dev), lik)
+            self.mean_module = gp.means.ZeroMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel())
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.lengthscale = ls
+    model.covar_module.outputscale = 1.3
+    mll = gp.mlls.ExactMarginalLogLikelihood(lik, model)
+    model.train(); lik.train()
+    with settings.max_preconditioner_size(rank), settings.probe_seed(7), settings.cg_tolerance(1e-3), settings.num_trace_samples(15):
+        out = mll(model(x.to(cuda_dev)), y.to(cuda_dev))
+        out.backward()
+    dd = (dvec.double() + 0.05)
+    Khat = K + torch.diag(dd)
+    Lc = torch.linalg.cholesky(Khat)
+    alpha = torch.cholesky_solve(y.double().unsqueeze(-1), Lc)[:, 0]
+    exact = -0.5 * (float(y.double() @ alpha) + float(2 * Lc.diagonal().log().sum()) + n * math.log(2 * math.pi)) / n
+    assert abs(out.item() - exact) < 0.02 * abs(exact) + 1e-3
+    # d mll / d second_noise = 0.5 (alpha^T alpha - tr(Khat^-1)) / n ; chain rule through softplus of the raw parameter
+    Kinv_tr = float(torch.cholesky_inverse(Lc).diagonal().sum())
+    g_exact = 0.5 * (float(alpha @ alpha) - Kinv_tr) / n
+    raw = lik.second_noise_covar.raw_noise
+    g_gpu = raw.grad.item() / torch.sigmoid(raw).item()
+    assert abs(g_gpu - g_exact) < 0.15 * abs(g_exact) + 1e-3     # stochastic trace estimate, 15 probes
