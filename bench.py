@@ -43,6 +43,9 @@ WORKLOADS = {
     # configs[2]: the 8-GPU strong-scaling case
     "c3": dict(name="ExactGP Matern-5/2 N=200000 d=20, row-sharded K.V + NCCL CG dots", n=200000, d=20,
                kind="matern52", lengthscale=2.0, outputscale=1.0, noise=0.1, probes=10, rank=100),
+    # configs[3]: batch of 16 independent exact GPs (own hyper-parameters per element), evaluated concurrently
+    "c4": dict(name="Batched ExactGP (batch=16) RBF N=10000 d=8 -- batched Krylov / inv_quad_logdet path", n=10000, d=8, kind="rbf",
+               lengthscale=0.9, outputscale=1.0, noise=0.1, probes=10, rank=100, batch=16),
     # small case for quick checks (not a BASELINE config)
     "small": dict(name="ExactGP RBF N=4000 d=3 (quick check, not a BASELINE config)", n=4000, d=3, kind="rbf", lengthscale=0.5,
                   outputscale=1.0, noise=0.1, probes=10, rank=15),
@@ -368,6 +371,76 @@ def result_config(w, world, m):
     }
 
 
+def run_c4(args, w):
+    """BASELINE configs[3]: batch of `batch` independent exact GPs through the public API (batch_shape kernels / likelihood /
+    MultivariateNormal.log_prob -> [B]); the elements run concurrently, one engine plan + CUDA stream each.  One step = one
+    batched MLL evaluation (all B problems); value counts evaluations of single problems per second."""
+    import torch
+
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, n, d = w["batch"], w["n"], w["d"]
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(B, n, d, generator=g)
+    Y = torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(B, n, generator=g)
+    bs = torch.Size([B])
+    lik = gp.likelihoods.GaussianLikelihood(batch_shape=bs).to(dev)
+    lik.noise = (w["noise"] * (1 + 0.05 * torch.arange(B))).unsqueeze(-1)
+
+    class Model(gp.models.ExactGP):
+        def __init__(self, tx, ty):
+            super().__init__(tx, ty, lik)
+            self.mean_module = gp.means.ZeroMean(batch_shape=bs)
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel(batch_shape=bs), batch_shape=bs)
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    Xd, Yd = X.to(dev), Y.to(dev)
+    model = Model(Xd, Yd).to(dev)
+    model.covar_module.base_kernel.lengthscale = (w["lengthscale"] * (1 + 0.02 * torch.arange(B))).reshape(B, 1, 1)
+    model.covar_module.outputscale = w["outputscale"] * (1 + 0.03 * torch.arange(B))
+    mll = gp.mlls.ExactMarginalLogLikelihood(lik, model)
+    model.train(); lik.train()
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        l2_flush.zero_()
+        with torch.no_grad(), settings.max_preconditioner_size(w["rank"]), settings.num_trace_samples(w["probes"]), \
+                settings.backend(args.backend), settings.probe_seed(1):
+            return mll(model(Xd), Yd)
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_step = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    # serial reference: the same B problems one after the other on one stream (what round 1 did)
+    from gpytorch_b200.operators import BatchLinearOperator
+    line = {
+        "metric": METRIC, "value": B * 1e3 / ms_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "batch": B, "parallelism": "single GPU, one plan + stream per batch element, 16 host threads",
+                   "kind": w["kind"], "precond_rank_requested": w["rank"], "num_probes": w["probes"],
+                   "l2_policy": "L2 flushed between timed steps by a 192 MiB memset inside the timed region",
+                   "step": "one batched MLL evaluation = 16 problems; value = single-problem evaluations per second",
+                   "mll_per_element": [float(v) for v in out.tolist()]},
+        "clocks": clocks, "e2e": None, "gpu_launches": None, "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -519,6 +592,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif args.workload == "c4":
+        run_c4(args, w)
     else:
         run_ours(args, w)
 

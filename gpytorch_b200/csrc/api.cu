@@ -108,6 +108,11 @@ extern "C" int gp_plan_destroy(gp_plan* p) {
                         &p->tmat_tmp, &p->misc, &p->misc2, &p->misc3, &p->pcdiag, &p->pcperm, &p->pcpos, &p->pcstate,
                         &p->gram, &p->cholC};
   for (auto* b : bufs) b->release();
+  if (p->ski) {
+    gp::DevBuf* sb[] = {&p->ski->first, &p->ski->wts, &p->ski->gridA, &p->ski->gridB, &p->ski->T, &p->ski->flag};
+    for (auto* b : sb) b->release();
+    delete p->ski;
+  }
   if (p->pinned) cudaFreeHost(p->pinned);
   delete p;
   return GP_OK;
@@ -116,6 +121,7 @@ extern "C" int gp_plan_destroy(gp_plan* p) {
 extern "C" int gp_plan_set_backend(gp_plan* p, int backend) {
   GP_REQUIRE(p != nullptr, GP_E_STATE, "null plan");
   GP_REQUIRE(backend >= GP_BACKEND_AUTO && backend <= GP_BACKEND_SIMT, GP_E_SHAPE, "bad backend %d", backend);
+  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_STATE, "the SKI backend is selected by gp_plan_set_ski");
   p->backend_req = backend;
   if (p->data_set && p->hypers_set) return pack_inputs(p);
   return GP_OK;
@@ -217,6 +223,7 @@ extern "C" int gp_time_kmv_kernel(gp_plan* p, const float* V, int64_t ldv, int t
   GP_CHECK(to_v16(p, V, ldv, t, p->n2, p->V16.as<float>()));
   if (p->backend == GP_BACKEND_TCGEN05) GP_CHECK(pack_v_tiles(p, p->V16.as<float>()));
   auto launch = [&]() -> int {
+    if (p->backend == GP_BACKEND_SKI) return ski_kmv_partials(p, p->V16.as<float>(), nullptr);
     return p->backend == GP_BACKEND_TCGEN05 ? kmv_tc_launch(p, nullptr) : kmv_simt_launch(p, p->V16.as<float>(), nullptr);
   };
   for (int i = 0; i < warmup; ++i) GP_CHECK(launch());
@@ -261,7 +268,7 @@ extern "C" int gp_mll(gp_plan* p, const float* y_minus_mean, const float* eps1, 
   int k = 0;
   double logdet_p = 0.0;
   const float* W = nullptr;
-  const bool want_precond = o->precond_rank > 0 && N >= o->min_precond_size;
+  const bool want_precond = o->precond_rank > 0 && N >= o->min_precond_size && p->backend != GP_BACKEND_SKI;
   float* Lt = nullptr;
   if (want_precond) {
     int rank = (int)std::min<int64_t>(o->precond_rank, N);

@@ -96,6 +96,14 @@ struct CgState {
 
 }  // namespace gp
 
+// SKI / KISS-GP backend state (ski.cu): grid geometry, compact interpolation data, grid work blocks, Toeplitz factors
+struct gp_ski_state {
+  int G[4] = {0, 0, 0, 0};
+  float lo[4] = {0, 0, 0, 0}, step[4] = {0, 0, 0, 0};
+  int64_t M = 0;
+  gp::DevBuf first, wts, gridA, gridB, T, flag;
+};
+
 struct gp_comm {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
@@ -136,6 +144,7 @@ struct gp_plan {
   gp::DevBuf cgU, cgR, cgZ, cgP, cgV, cgPfull, red, sums, qtr, state, tmat_tmp, misc, misc2, misc3;
   gp::DevBuf pcdiag, pcperm, pcpos, pcstate, gram, cholC;
   gp_comm* comm = nullptr;
+  gp_ski_state* ski = nullptr;   // non-null: backend == GP_BACKEND_SKI
   void* pinned = nullptr;  // small pinned host scratch
   long long* tc_trace = nullptr;  // optional device buffer [256][8] for the pipeline event trace of CTA (0,0)
 };
@@ -153,6 +162,8 @@ int kmv_simt_launch(gp_plan* p, const float* V16, const int* done_flag);
 int kmv_tc_launch(gp_plan* p, const int* done_flag);
 int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t, int add_noise);
 int choose_geometry(gp_plan* p);
+int ski_pack(gp_plan* p);                                               // ski.cu
+int ski_kmv_partials(gp_plan* p, const float* V16, const int* done_flag);
 
 __host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -105,6 +105,7 @@ int kmv_simt_launch(gp_plan* p, const float* V16, const int* done_flag) {
 }
 
 int kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
+  if (p->backend == GP_BACKEND_SKI) return ski_kmv_partials(p, V16, done_flag);
   if (p->backend == GP_BACKEND_TCGEN05) {
     GP_CHECK(pack_v_tiles(p, V16));
     return kmv_tc_launch(p, done_flag);
@@ -326,6 +327,7 @@ using namespace gp;
 
 extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, int64_t ldo) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "row extraction is not available for the SKI backend");
   GP_REQUIRE(m >= 0 && ldo >= p->n2, GP_E_SHAPE, "bad krows shape");
   if (m == 0) return GP_OK;
   const float* Z1 = p->same ? p->Z2.as<float>() + p->row_begin * p->DP : p->Z1.as<float>();
@@ -344,6 +346,7 @@ extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, i
 
 extern "C" int gp_kdiag(gp_plan* p, float* OUT) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "the diagonal is not available for the SKI backend");
   if (p->same) {
     // stationary kernels: k(x,x) = outputscale (lazy_evaluated_kernel_tensor.py:107-133 evaluates kernel(diag=True))
     fill_kernel<<<(unsigned)cdiv(p->row_count, 256), 256, 0, p->stream>>>(OUT, p->row_count, p->outputscale);
@@ -368,6 +371,7 @@ extern "C" int gp_kdiag(gp_plan* p, float* OUT) {
 extern "C" int gp_bilinear_grad(gp_plan* p, const float* Lf, int64_t ldl, const float* Rt, int64_t ldr, int s,
                                 double* grad_ls, double* grad_os) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
+  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "hyper-parameter gradients are not available for the SKI backend yet");
   GP_REQUIRE(s >= 1, GP_E_SHAPE, "s must be >= 1");
   const bool ard = p->ls.size() > 1;
   const int nout = 1 + (ard ? p->d : 1);

@@ -71,6 +71,11 @@ __global__ void lz_gemv_n_kernel(const float* __restrict__ Qt, int m, int64_t n,
   }
 }
 
+__global__ void lz_sqrt_kernel(double* v) { *v = sqrt(*v); }
+
+int nccl_allreduce_double(gp_comm* c, double* buf, size_t count, cudaStream_t st);   // comm.cu
+int nccl_allgather_float(gp_comm* c, float* buf, size_t count_per_rank, cudaStream_t st);
+
 }  // namespace gp
 
 using namespace gp;
@@ -78,14 +83,21 @@ using namespace gp;
 extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol, float* Qt, float* T, int* J_out) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->same, GP_E_SHAPE, "Lanczos needs a square operator");
-  GP_REQUIRE(!(p->comm && p->comm->world > 1), GP_E_SHAPE, "gp_lanczos is single-GPU in this version");
   GP_REQUIRE(max_iter >= 1, GP_E_SHAPE, "max_iter must be >= 1");
   cudaStream_t st = p->stream;
-  const int64_t n = p->n2;
-  const int num_iter = (int)std::min<int64_t>(max_iter, n);
+  // row-sharded runs (one process per GPU): every vector (INIT, the basis rows of Qt, r) holds this rank's rows only; the
+  // products all-gather the current basis vector, the dots / Gram-Schmidt coefficients are all-reduced (fp64)
+  const bool sharded = p->comm && p->comm->world > 1;
+  const int64_t N = p->n2;
+  const int64_t n = p->row_count;
+  GP_REQUIRE(!sharded || (n * p->comm->world == N && p->row_begin == (int64_t)p->comm->rank * n), GP_E_SHAPE,
+             "row-sharded Lanczos needs equal contiguous shards");
+  const int num_iter = (int)std::min<int64_t>(max_iter, N);
   const int G = 2 * p->n_sm;
-  GP_CHECK(p->misc.ensure(sizeof(float) * n + sizeof(double) * (G + num_iter + 16)));
-  GP_CHECK(p->V16.ensure(sizeof(float) * n * TP));
+  GP_CHECK(p->misc.ensure(sizeof(float) * (n + 2) + sizeof(double) * (G + num_iter + 16)));
+  GP_CHECK(p->V16.ensure(sizeof(float) * N * TP));
+  if (sharded) GP_CHECK(p->cgPfull.ensure(sizeof(float) * N));
+  float* qfull = sharded ? p->cgPfull.as<float>() : nullptr;
   float* r = p->misc.as<float>();
   double* part = reinterpret_cast<double*>(r + ((n + 1) / 2) * 2);
   double* ds = part + G;            // device scalars: [0] alpha [1] beta / norm
@@ -95,11 +107,21 @@ extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol
 
   auto dot = [&](const float* a, const float* b, double* out, int do_sqrt) {
     lz_dot_kernel<<<G, 256, 0, st>>>(a, b, n, part);
-    lz_sum_kernel<<<1, 32, 0, st>>>(part, G, out, do_sqrt);
+    lz_sum_kernel<<<1, 32, 0, st>>>(part, G, out, sharded ? 0 : do_sqrt);
     p->launches += 2;
+    if (sharded) {
+      nccl_allreduce_double(p->comm, out, 1, st);
+      if (do_sqrt) { lz_sqrt_kernel<<<1, 1, 0, st>>>(out); p->launches++; }
+    }
   };
   auto matvec = [&](const float* q, float* out) -> int {
-    GP_CHECK(to_v16(p, q, 1, 1, n, p->V16.as<float>()));
+    const float* qv = q;
+    if (sharded) {
+      GP_CUDA(cudaMemcpyAsync(qfull + p->row_begin, q, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+      GP_CHECK(nccl_allgather_float(p->comm, qfull, (size_t)n, st));
+      qv = qfull;
+    }
+    GP_CHECK(to_v16(p, qv, 1, 1, N, p->V16.as<float>()));
     GP_CHECK(kmv_partials(p, p->V16.as<float>(), nullptr));
     return kmv_finish_user(p, p->V16.as<float>(), out, 1, 1, 1);
   };
@@ -108,8 +130,12 @@ extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol
     GP_CUDA(cudaStreamSynchronize(st));
     return GP_OK;
   };
-  auto reorth = [&](int m) {  // r -= Q[:m] (Q[:m]^T r)
+  auto gemv_t = [&](int m) {
     lz_gemv_t_kernel<<<m, 256, 0, st>>>(Qt, n, r, cvec);
+    if (sharded) nccl_allreduce_double(p->comm, cvec, (size_t)m, st);
+  };
+  auto reorth = [&](int m) {  // r -= Q[:m] (Q[:m]^T r)
+    gemv_t(m);
     lz_gemv_n_kernel<<<G, 256, sizeof(float) * ((m + 3) & ~3), st>>>(Qt, m, n, cvec, r);
     p->launches += 2;
   };
@@ -147,7 +173,7 @@ extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol
       lz_scale_kernel<<<G, 256, 0, st>>>(r, ds + 1, n, r);
       p->launches++;
       // inner products after normalisation
-      lz_gemv_t_kernel<<<k + 1, 256, 0, st>>>(Qt, n, r, cvec);
+      gemv_t(k + 1);
       p->launches++;
       GP_CUDA(cudaMemcpyAsync(h, ds, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
       GP_CUDA(cudaMemcpyAsync(h + 8, cvec, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, st));
@@ -164,7 +190,7 @@ extern "C" int gp_lanczos(gp_plan* p, const float* INIT, int max_iter, float tol
         reorth(k + 1);
         dot(r, r, ds + 2, 1);
         lz_scale_kernel<<<G, 256, 0, st>>>(r, ds + 2, n, r);
-        lz_gemv_t_kernel<<<k + 1, 256, 0, st>>>(Qt, n, r, cvec);
+        gemv_t(k + 1);
         p->launches += 2;
         GP_CUDA(cudaMemcpyAsync(h + 8, cvec, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, st));
         GP_CUDA(cudaStreamSynchronize(st));

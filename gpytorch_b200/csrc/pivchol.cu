@@ -499,6 +499,7 @@ using namespace gp;
 extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float* Lt, int64_t* piv, int* rank_out) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->same, GP_E_SHAPE, "pivoted Cholesky needs a square operator");
+  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "pivoted Cholesky is not available for the SKI backend");
   const int64_t n = p->n2;
   GP_REQUIRE(n < (int64_t)1 << 31, GP_E_SHAPE, "n too large");
   rank = (int)std::min<int64_t>(rank, n);

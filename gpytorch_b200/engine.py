@@ -94,6 +94,17 @@ class Plan:
             check(self.lib.gp_plan_set_hypers(self._h, KIND[kind], arr, len(ls), float(outputscale), float(noise)))
         return self
 
+    def set_ski(self, grid_sizes, grid_lo, grid_step):
+        """SKI / KISS-GP: the operator becomes W (T_0 x ... x T_{d-1}) W^T on a regular grid (first node grid_lo[i], spacing
+        grid_step[i], grid_sizes[i] nodes per dimension).  Call before set_hypers."""
+        d = len(grid_sizes)
+        gs = (C.c_int * d)(*[int(v) for v in grid_sizes])
+        lo = (C.c_float * d)(*[float(v) for v in grid_lo])
+        st = (C.c_float * d)(*[float(v) for v in grid_step])
+        with torch.cuda.device(self.device):
+            check(self.lib.gp_plan_set_ski(self._h, gs, lo, st, d))
+        return self
+
     def set_noise_diag(self, diag: torch.Tensor | None):
         """Per-row noise variances (FixedNoiseGaussianLikelihood): K_hat = K + diag(d).  None restores the scalar noise."""
         if diag is None:
@@ -108,7 +119,7 @@ class Plan:
     def info(self):
         b, s, k, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(self.lib.gp_plan_info(self._h, C.byref(b), C.byref(s), C.byref(k), C.byref(m)))
-        return {"backend": {1: "tcgen05", 2: "simt"}.get(b.value, "?"), "nsplit": s.value, "kpad": k.value, "n_sm": m.value}
+        return {"backend": {1: "tcgen05", 2: "simt", 3: "ski"}.get(b.value, "?"), "nsplit": s.value, "kpad": k.value, "n_sm": m.value}
 
     def time_kmv_kernel(self, v: torch.Tensor, warmup: int = 3, reps: int = 20) -> float:
         """Average device time (ms) of ONE launch of the fused K.V kernel alone (CUDA events on the plan stream)."""
@@ -207,9 +218,11 @@ class Plan:
         return out.value
 
     def lanczos(self, init: torch.Tensor, max_iter: int, tol: float = 1e-5):
-        """Returns (Q [n, J], T [J, J])."""
+        """Returns (Q [n_local, J], T [J, J]); on a row-sharded plan init / Q hold this rank's rows."""
         init = init.contiguous()
-        qt = torch.zeros(max_iter, self.n2, device=self.device, dtype=torch.float32)
+        if init.numel() != self.row_count:
+            raise RuntimeError(f"Lanczos start vector has {init.numel()} entries, the plan owns {self.row_count} rows")
+        qt = torch.zeros(max_iter, self.row_count, device=self.device, dtype=torch.float32)
         tm = torch.zeros(max_iter, max_iter, device=self.device, dtype=torch.float32)
         j = C.c_int()
         check(self.lib.gp_lanczos(self._h, _ptr(init), int(max_iter), float(tol), _ptr(qt), _ptr(tm), C.byref(j)))

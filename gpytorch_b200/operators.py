@@ -32,12 +32,21 @@ def _as_list(ls: torch.Tensor):
 # training loop does not re-allocate every step.  Hyper-parameters / data are re-packed whenever a new operator
 # first touches a cached plan.
 _PLAN_CACHE: "dict[tuple, Plan]" = {}
-_PLAN_CACHE_MAX = 6
+_PLAN_CACHE_MAX = 64          # a batch of 16 independent operators (+ their cross-covariances) must fit
+_PLAN_LOCK = __import__("threading").RLock()   # BatchLinearOperator drives the cache from worker threads
 
 
 def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
+    if not x1.is_cuda:
+        raise RuntimeError("x1 must live on a CUDA device: gpytorch_b200 has no CPU path")
+    with _PLAN_LOCK:
+        return _get_plan_locked(x1, x2, backend, row_begin, row_count, comm)
+
+
+def _get_plan_locked(x1, x2, backend, row_begin, row_count, comm) -> Plan:
+    # a plan enqueues on the stream that was current when it was created: the stream is part of the identity
     key = (x1.data_ptr(), tuple(x1.shape), x1.stride(0), None if x2 is None else (x2.data_ptr(), tuple(x2.shape), x2.stride(0)),
-           backend, str(x1.device), row_begin, row_count, id(comm))
+           backend, str(x1.device), row_begin, row_count, id(comm), torch.cuda.current_stream(x1.device).cuda_stream)
     plan = _PLAN_CACHE.pop(key, None)
     src_versions = (x1._version, None if x2 is None else x2._version)
     if plan is not None and plan._src_versions != src_versions:
@@ -47,7 +56,7 @@ def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
         plan.x2 = plan.x1 if x2 is None else x2.contiguous()
         plan.refresh_data()
     if plan is None:
-        plan = Plan(x1, x2, backend=backend, row_begin=row_begin, row_count=row_count, comm=comm)
+        plan = Plan(x1, x2, backend="auto" if backend.startswith("ski:") else backend, row_begin=row_begin, row_count=row_count, comm=comm)
         plan._hyp_key = None
     plan._src_versions = src_versions
     _PLAN_CACHE[key] = plan  # most recently used last
@@ -57,8 +66,9 @@ def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
 
 
 def clear_plan_cache():
-    while _PLAN_CACHE:
-        _PLAN_CACHE.popitem()[1].close()
+    with _PLAN_LOCK:
+        while _PLAN_CACHE:
+            _PLAN_CACHE.popitem()[1].close()
 
 
 class ConstantDiagLinearOperator:
@@ -264,6 +274,49 @@ class KernelLinearOperator:
         """(d/d lengthscale, d/d outputscale) of sum(left * (K @ right)); lazy_evaluated_kernel_tensor.py:69-105."""
         gl, go = self.plan(getattr(self, "_last_noise", 0.0)).bilinear_grad(left, right)
         return torch.tensor(gl, device=self.device, dtype=self.dtype), torch.tensor(go, device=self.device, dtype=self.dtype)
+
+
+class SKIKernelLinearOperator(KernelLinearOperator):
+    """K_ski = s W (T_0 x ... x T_{d-1}) W^T (kernels/grid_interpolation_kernel.py:132-213): the engine's SKI backend -- cubic
+    interpolation weights kept in compact per-dimension form, Kronecker / Toeplitz grid covariance applied mode by mode."""
+
+    def __init__(self, x1, kind, lengthscale, outputscale, grid_sizes, grid_lo, grid_step):
+        super().__init__(x1, None, kind, lengthscale, outputscale)
+        self.grid_sizes, self.grid_lo, self.grid_step = tuple(grid_sizes), tuple(grid_lo), tuple(grid_step)
+
+    def plan(self, noise=0.0) -> Plan:
+        if self._plan is None:
+            key = "ski:" + repr((self.grid_sizes, self.grid_lo, self.grid_step))
+            self._plan = _get_plan(self.x1, None, key, 0, 0, None)
+            if getattr(self._plan, "_ski_key", None) != key:
+                self._plan.set_ski(self.grid_sizes, self.grid_lo, self.grid_step)
+                self._plan._ski_key = key
+                self._plan._hyp_key = None
+        if torch.is_tensor(noise):
+            ls, os_, nz, _ = self._host_hypers(noise)
+        else:
+            ls, os_, _, _ = self._host_hypers(None)
+            nz = float(noise)
+        hk = (self.kind, tuple(ls), os_, nz)
+        if getattr(self._plan, "_hyp_key", None) != hk:
+            self._plan.set_hypers(self.kind, ls, os_, nz)
+            self._plan._hyp_key = hk
+        return self._plan
+
+    def detach(self):
+        return SKIKernelLinearOperator(self.x1, self.kind, self.lengthscale.detach(), self.outputscale.detach(), self.grid_sizes,
+                                       self.grid_lo, self.grid_step)
+
+    def to_dense(self):
+        n = self.x1.size(0)
+        eye = torch.eye(n, device=self.device, dtype=torch.float32)
+        return torch.cat([self.plan().kmv(eye[:, c0:c0 + 16].contiguous()) for c0 in range(0, n, 16)], -1)
+
+    def diagonal(self, dim1=-2, dim2=-1):
+        raise NotImplementedError("diagonal of the SKI operator")
+
+    def __getitem__(self, index):
+        raise NotImplementedError("slicing the SKI operator")
 
 
 class _KernelMatmul(torch.autograd.Function):
@@ -494,6 +547,119 @@ class AddedDiagLinearOperator:
         evecs = evecs * mask
         evals = evals.masked_fill(~mask, 1.0)
         return (q.double() @ (evecs / evals.sqrt())).float()
+
+
+class BatchLinearOperator:
+    """One leading batch dimension of independent operators (BASELINE config 4: batch = 16, independent hyper-parameters per
+    element; the reference broadcasts every LinearOperator op over leading dims, kernels/kernel.py:119-121,
+    distributions/multivariate_normal.py:236-245).  Each element owns an engine plan on its own CUDA stream; solver calls
+    (inv_quad_logdet / solve) of all elements run concurrently from a thread pool (the C ABI releases the GIL), so the small
+    per-element grids and launch chains overlap on the device."""
+
+    _pool = None
+
+    def __init__(self, ops):
+        self.ops = list(ops)
+        first = self.ops[0]
+        self._mshape = first.shape
+
+    @property
+    def batch_shape(self):
+        return torch.Size([len(self.ops)])
+
+    @property
+    def shape(self):
+        return torch.Size([len(self.ops), *self._mshape])
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    @property
+    def device(self):
+        return self.ops[0].device
+
+    @property
+    def dtype(self):
+        return self.ops[0].dtype
+
+    def evaluate_kernel(self):
+        return self
+
+    def __getitem__(self, b):
+        return self.ops[b]
+
+    def __add__(self, other):
+        # batched homoskedastic noise: ConstantDiagLinearOperator with diag_value [B, 1]
+        if isinstance(other, ConstantDiagLinearOperator):
+            dv = other.diag_value
+            outs = []
+            for b, op in enumerate(self.ops):
+                d_b = dv[b] if dv.dim() >= 2 or (dv.dim() == 1 and dv.numel() == len(self.ops) and dv.numel() > 1) else dv
+                outs.append(op + ConstantDiagLinearOperator(d_b.reshape(-1)[:1], other.n))
+            return BatchLinearOperator(outs)
+        if isinstance(other, DiagLinearOperator):
+            dv = other.diag_vec
+            return BatchLinearOperator([op + DiagLinearOperator(dv[b] if dv.dim() == 2 else dv) for b, op in enumerate(self.ops)])
+        raise NotImplementedError("BatchLinearOperator only adds a (Constant)DiagLinearOperator")
+
+    def _map(self, fn):
+        """Run fn(b, op) for every element concurrently, element b on its own stream."""
+        import concurrent.futures as cf
+
+        B = len(self.ops)
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        streams = _batch_streams(dev, B)
+        grad = torch.is_grad_enabled()
+        ctxs = settings.snapshot()
+
+        def work(b):
+            with torch.cuda.device(dev), torch.cuda.stream(streams[b]), torch.set_grad_enabled(grad), settings.restore(ctxs):
+                return fn(b, self.ops[b])
+
+        for st in streams:
+            st.wait_stream(main)
+        if BatchLinearOperator._pool is None:
+            BatchLinearOperator._pool = cf.ThreadPoolExecutor(max_workers=16, thread_name_prefix="gpbatch")
+        outs = list(BatchLinearOperator._pool.map(work, range(B)))
+        for st in streams:
+            main.wait_stream(st)
+        return outs
+
+    def matmul(self, rhs):
+        return torch.stack(self._map(lambda b, op: op.matmul(rhs[b] if rhs.dim() == 3 else rhs)))
+
+    __matmul__ = matmul
+
+    def diagonal(self, dim1=-2, dim2=-1):
+        return torch.stack([op.diagonal() for op in self.ops])
+
+    def to_dense(self):
+        return torch.stack([op.to_dense() for op in self.ops])
+
+    def solve(self, rhs, lhs=None):
+        return torch.stack(self._map(lambda b, op: op.solve(rhs[b] if rhs.dim() >= 2 and rhs.size(0) == len(self.ops) else rhs)))
+
+    def inv_quad_logdet(self, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True):
+        def one(b, op):
+            r = None if inv_quad_rhs is None else inv_quad_rhs[b]
+            return op.inv_quad_logdet(r, logdet=logdet, reduce_inv_quad=reduce_inv_quad)
+
+        outs = self._map(one)
+        iq = torch.stack([o[0] for o in outs])
+        ld = torch.stack([o[1] for o in outs]) if logdet else None
+        return iq, ld
+
+
+_BATCH_STREAMS = {}
+
+
+def _batch_streams(dev, n):
+    key = str(dev)
+    pool = _BATCH_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
 
 
 def _cg_tolerance():

@@ -124,3 +124,29 @@ class backend(_value_context):
 class probe_seed(_value_context):
     """Seed of the base samples for the SLQ probes (None = draw from torch's global CUDA generator)."""
     _global_value = None
+
+
+# ---- propagation into worker threads (operators.BatchLinearOperator) ----
+# The knobs are process-wide class attributes (as in the reference, settings.py:84-144), so worker threads already see the values
+# set by the calling thread's `with` blocks; snapshot() / restore() exist so that the hand-over is explicit and testable.
+def snapshot():
+    import sys
+    mod = sys.modules[__name__]
+    out = {}
+    for name, obj in vars(mod).items():
+        if isinstance(obj, type) and issubclass(obj, _value_context) and obj is not _value_context:
+            out[name] = ("v", obj.value())
+        elif isinstance(obj, type) and issubclass(obj, _feature_flag) and obj is not _feature_flag:
+            out[name] = ("f", obj._state)
+    return out
+
+
+class restore:
+    def __init__(self, snap):
+        self.snap = snap
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

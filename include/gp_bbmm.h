@@ -45,7 +45,7 @@ enum { GP_RBF = 0, GP_MATERN12 = 1, GP_MATERN32 = 2, GP_MATERN52 = 3 };
 
 /* which fused K.V kernel runs: GP_BACKEND_TCGEN05 = tcgen05/TMEM/bulk-TMA 3xTF32 kernel,
  * GP_BACKEND_SIMT = fp32 CUDA-core kernel (bring-up / cross-check / d > 41). */
-enum { GP_BACKEND_AUTO = 0, GP_BACKEND_TCGEN05 = 1, GP_BACKEND_SIMT = 2 };
+enum { GP_BACKEND_AUTO = 0, GP_BACKEND_TCGEN05 = 1, GP_BACKEND_SIMT = 2, GP_BACKEND_SKI = 3 /* set by gp_plan_set_ski */ };
 
 typedef struct gp_plan gp_plan;   /* opaque: repacked X, workspaces, stream, comm */
 typedef struct gp_comm gp_comm;   /* opaque: NCCL communicator for row-sharded runs */
@@ -80,6 +80,13 @@ int gp_plan_set_hypers(gp_plan* plan, int kind, const float* lengthscale, int n_
  * noise_models.py:150-190): K_hat = K + diag(d).  `diag` is a device pointer to n2 floats (caller-owned, must outlive the plan's
  * use of it) that replaces the scalar noise in every product / solve / preconditioner / probe; NULL restores the scalar. */
 int gp_plan_set_noise_diag(gp_plan* plan, const float* diag, int64_t n);
+
+/* SKI / KISS-GP (kernels/grid_interpolation_kernel.py:132-213, kernels/grid_kernel.py:107-177, utils/interpolation.py:15-167):
+ * the plan's operator becomes K_ski = W (T_0 x ... x T_{d-1}) W^T with cubic interpolation onto a regular grid; grid_lo[i] /
+ * grid_step[i] are the first node and the spacing of dimension i (utils/grid.py:142-180), grid_sizes[i] in [4, 128], d <= 4.
+ * Call after gp_plan_set_data (square operator); products, mBCG, SLQ, gp_mll (without preconditioner) and gp_lanczos then run
+ * on the interpolated operator.  Out-of-bounds inputs fail like the reference ("Received data that was out of bounds ..."). */
+int gp_plan_set_ski(gp_plan* plan, const int* grid_sizes, const float* grid_lo, const float* grid_step, int d);
 
 /* ---- kernel seam (LazyEvaluatedKernelTensor, lazy/lazy_evaluated_kernel_tensor.py) --- */
 

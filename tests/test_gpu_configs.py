@@ -339,3 +339,75 @@ def test_fixed_noise_likelihood_per_row_diagonal(Plan, cuda_dev):
     raw = lik.second_noise_covar.raw_noise
     g_gpu = raw.grad.item() / torch.sigmoid(raw).item()
     assert abs(g_gpu - g_exact) < 0.15 * abs(g_exact) + 1e-3     # stochastic trace estimate, 15 probes
+
+
+def test_c4_batched_exact_gp_through_api(cuda_dev):
+    """BASELINE config 4 shape (batch of independent exact GPs, own hyper-parameters per element, test/examples/
+    test_batch_gp_regression.py:72-140): Kernel / ScaleKernel / GaussianLikelihood / ConstantMean with batch_shape, inputs
+    [B, n, d], MultivariateNormal.log_prob -> [B].  Elements run concurrently (one engine plan and CUDA stream each); every
+    element must equal its own stand-alone evaluation bit for bit, and the oracle within the Krylov tolerance rule."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    B, n, d, rank = 4, 2400, 8, 40
+    g = torch.Generator().manual_seed(4)
+    X = torch.rand(B, n, d, generator=g)
+    Y = torch.sin(2 * X.sum(-1)) + 0.1 * torch.randn(B, n, generator=g)
+    ls = torch.tensor([0.8 + 0.2 * i for i in range(B)])
+    osc = torch.tensor([1.0 + 0.5 * i for i in range(B)])
+    nz = torch.tensor([0.05 * (i + 1) for i in range(B)])
+    bs = torch.Size([B])
+    lik = gp.likelihoods.GaussianLikelihood(batch_shape=bs).to(cuda_dev)
+    lik.noise = nz.unsqueeze(-1)
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(X.to(cuda_dev), Y.to(cuda_dev), lik)
+            self.mean_module = gp.means.ConstantMean(batch_shape=bs)
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel(batch_shape=bs), batch_shape=bs)
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.lengthscale = ls.reshape(B, 1, 1)
+    model.covar_module.outputscale = osc
+    assert tuple(model.covar_module.base_kernel.raw_lengthscale.shape) == (B, 1, 1)       # kernel.py:213-219
+    assert tuple(lik.noise_covar.raw_noise.shape) == (B, 1)
+    mll = gp.mlls.ExactMarginalLogLikelihood(lik, model)
+    model.train(); lik.train()
+    with torch.no_grad(), settings.max_preconditioner_size(rank), settings.probe_seed(11):
+        out = mll(model(X.to(cuda_dev)), Y.to(cuda_dev))
+        out2 = mll(model(X.to(cuda_dev)), Y.to(cuda_dev))
+    assert tuple(out.shape) == (B,)
+    assert torch.equal(out, out2)                                  # concurrent execution is still deterministic
+    # element by element: stand-alone model with the same hyper-parameters and probe seed
+    for i in range(B):
+        lik1 = gp.likelihoods.GaussianLikelihood().to(cuda_dev)
+        lik1.noise = float(nz[i])
+
+        class M1(gp.models.ExactGP):
+            def __init__(self):
+                super().__init__(X[i].to(cuda_dev), Y[i].to(cuda_dev), lik1)
+                self.mean_module = gp.means.ConstantMean()
+                self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel())
+
+            def forward(self, xx):
+                return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+        m1 = M1().to(cuda_dev)
+        m1.covar_module.base_kernel.lengthscale = float(ls[i])
+        m1.covar_module.outputscale = float(osc[i])
+        m1.train(); lik1.train()
+        with torch.no_grad(), settings.max_preconditioner_size(rank), settings.probe_seed(11):
+            o1 = gp.mlls.ExactMarginalLogLikelihood(lik1, m1)(m1(X[i].to(cuda_dev)), Y[i].to(cuda_dev))
+        assert o1.item() == out[i].item()
+        dense = om.mll_cholesky("rbf", X[i].double(), Y[i].double(), 0.0, float(ls[i]), float(osc[i]), float(nz[i]))
+        assert abs(out[i].item() - dense.mll) < 0.02 * abs(dense.mll) + 2e-3
+    # gradients flow to the batched parameters
+    with settings.max_preconditioner_size(rank), settings.probe_seed(11):
+        loss = -mll(model(X.to(cuda_dev)), Y.to(cuda_dev)).sum()
+        loss.backward()
+    gl = model.covar_module.base_kernel.raw_lengthscale.grad
+    assert gl is not None and tuple(gl.shape) == (B, 1, 1) and torch.isfinite(gl).all() and (gl != 0).all()
+    assert lik.noise_covar.raw_noise.grad is not None and torch.isfinite(lik.noise_covar.raw_noise.grad).all()

@@ -1,0 +1,113 @@
+"""GPU parity of the SKI / KISS-GP backend (csrc/ski.cu; BASELINE configs[4]) against the pinned CPU
+oracle (oracle/ski.py: interpolation checked against outputs of the reference's own code, tests/golden/ski_golden.npz).
+Tolerances: products rel-l2 <= 2e-5 (fp32 interpolation weights and mode products, atomics in arbitrary order; the oracle runs in
+fp64), MLL by the Krylov rule of tests/test_gpu_configs.py."""
+import math
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import linalg as ol, mll as om, ski  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def _grid(sizes, bounds):
+    axes = ski.create_grid(sizes, bounds, dtype=torch.float32)
+    return axes, [float(a[0]) for a in axes], [float(a[1] - a[0]) for a in axes]
+
+
+@pytest.mark.parametrize("d,sizes", [(1, [24]), (2, [20, 16]), (3, [20, 16, 12]), (3, [9, 33, 7])])
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_ski_matmul_matches_oracle(cuda_dev, d, sizes, kind):
+    from gpytorch_b200.engine import Plan
+
+    g = torch.Generator().manual_seed(d * 10 + len(kind))
+    n, t = 3000, 11
+    bounds = [(0.0, 1.0)] * d
+    axes, lo, step = _grid(sizes, bounds)
+    x = torch.rand(n, d, generator=g)
+    # points inside the first / last grid cell (one-hot snapping, interpolation.py:84-131) and exactly on nodes
+    x[:20] = torch.rand(20, d, generator=g) * torch.tensor(step) - torch.tensor(step)            # first cell: [lo, lo + step)
+    x[20:40] = torch.tensor([float(a[-1]) for a in axes]) - torch.rand(20, d, generator=g) * torch.tensor(step) * 0.999
+    x[40] = torch.tensor([float(a[3]) for a in axes])
+    v = torch.randn(n, t, generator=g)
+    ls = 0.3
+    ref = ski.ski_matmul(kind, x.double(), [a.double() for a in axes], ls, 1.7, v.double())
+    p = Plan(x.to(cuda_dev)).set_ski(sizes, lo, step).set_hypers(kind, ls, 1.7, 0.2)
+    assert p.info()["backend"] == "ski"
+    out = p.kmv(v.to(cuda_dev))
+    assert rel(out, ref) < 2e-5
+    assert rel(p.kmv(v.to(cuda_dev), add_noise=True), ref + 0.2 * v.double()) < 2e-5
+    # symmetry of the interpolated operator
+    u = torch.randn(n, t, generator=g)
+    a = (u.double() * out.double().cpu()).sum()
+    b = (p.kmv(u.to(cuda_dev)).double().cpu() * v.double()).sum()
+    assert abs(a - b) <= 1e-4 * abs(a)
+    p.close()
+
+
+def test_ski_out_of_bounds_is_rejected_like_the_reference(cuda_dev):
+    from gpytorch_b200.engine import Plan
+
+    axes, lo, step = _grid([10, 10], [(0.0, 1.0)] * 2)
+    x = torch.rand(100, 2)
+    x[5, 1] = 1.5
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        Plan(x.to(cuda_dev)).set_ski([10, 10], lo, step).set_hypers("rbf", 0.3, 1.0, 0.1)
+
+
+def test_ski_mll_matches_oracle_and_api(cuda_dev):
+    """MLL of the interpolated operator (no preconditioner: Rademacher probes) against the oracle's mBCG run on the dense K_ski,
+    then the same through ScaleKernel(GridInterpolationKernel(RBFKernel())) + ExactMarginalLogLikelihood."""
+    from gpytorch_b200.engine import Plan
+
+    n, d, sizes, ls, osc, nz = 2500, 2, [30, 30], 0.25, 1.4, 0.05
+    x, y = om.synthetic_problem(n, d, 5, torch.float32)
+    axes, lo, step = _grid(sizes, [(0.0, 1.0)] * d)
+    Kd = ski.ski_matmul("rbf", x.double(), [a.double() for a in axes], ls, osc, torch.eye(n, dtype=torch.float64))
+    Kd = 0.5 * (Kd + Kd.t())
+    pn = om.make_probe_noise(n, 15, 10, 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o64 = om.mll_bbmm("rbf", x.double(), y.double(), 0.0, ls, osc, nz, tuple(a.double() for a in pn), precond_size=0, K=Kd)
+        o32 = om.mll_bbmm("rbf", x, y, 0.0, ls, osc, nz, pn, precond_size=0, K=Kd.float())
+    p = Plan(x.to(cuda_dev)).set_ski(sizes, lo, step).set_hypers("rbf", ls, osc, nz)
+    res, sol = p.mll(y.to(cuda_dev), pn[0].to(cuda_dev), pn[1].to(cuda_dev), pn[2].to(cuda_dev), 10, 15, 2000, want_solve=True)
+    assert res.precond_rank == 0 and res.cg_iters == o64.iters
+    assert abs(res.inv_quad - o64.inv_quad) <= max(2e-4 * abs(o64.inv_quad), 3 * abs(o32.inv_quad - o64.inv_quad))
+    assert abs(res.logdet - o64.logdet) <= max(2e-4 * abs(o64.logdet), 3 * abs(o32.logdet - o64.logdet))
+    p.close()
+    # public API
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    lik = gp.likelihoods.GaussianLikelihood().to(cuda_dev)
+    lik.noise = nz
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(x.to(cuda_dev), y.to(cuda_dev), lik)
+            self.mean_module = gp.means.ZeroMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.GridInterpolationKernel(gp.kernels.RBFKernel(), grid_size=30, num_dims=2,
+                                                                                       grid_bounds=[(0.0, 1.0)] * 2))
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.base_kernel.lengthscale = ls
+    model.covar_module.outputscale = osc
+    model.train(); lik.train()
+    with torch.no_grad(), settings.probe_seed(3), settings.cg_tolerance(1e-3), settings.num_trace_samples(15), settings.max_preconditioner_size(0):
+        out = gp.mlls.ExactMarginalLogLikelihood(lik, model)(model(x.to(cuda_dev)), y.to(cuda_dev))
+    Lc = torch.linalg.cholesky(Kd + nz * torch.eye(n, dtype=torch.float64))
+    alpha = torch.cholesky_solve(y.double().unsqueeze(-1), Lc)[:, 0]
+    exact = -0.5 * (float(y.double() @ alpha) + float(2 * Lc.diagonal().log().sum()) + n * math.log(2 * math.pi)) / n
+    assert abs(out.item() - exact) < 0.03 * abs(exact) + 2e-3

@@ -73,6 +73,15 @@ for (n, d, kind, ls, krank) in cases:
     serr = rel(sol, s1[rb:rb + rc])
     check(serr < 5e-4, f"solve shard rel diff {serr}")
     check(rel(kv, kv1[rb:rb + rc]) < 2e-6, f"K.V shard vs single-GPU rows {rel(kv, kv1[rb:rb + rc])}")
+    # Lanczos (LOVE root decomposition, exact_prediction_strategies.py:268-272) on the shard: same tridiagonal, same basis rows
+    g2 = torch.Generator().manual_seed(5)
+    init = torch.randn(n, generator=g2)
+    ql, tl = p.lanczos(init[rb:rb + rc].contiguous().to(dev), 25)
+    q1, t1 = p1.lanczos(init.to(dev), 25)
+    check(tuple(tl.shape) == tuple(t1.shape), f"Lanczos size {tuple(tl.shape)} vs {tuple(t1.shape)}")
+    if tuple(tl.shape) == tuple(t1.shape):
+        check(rel(tl, t1) < 2e-4, f"Lanczos T sharded vs single {rel(tl, t1)}")
+        check(rel(ql[:, :8], q1[rb:rb + rc, :8]) < 2e-3, f"Lanczos Q rows {rel(ql[:, :8], q1[rb:rb + rc, :8])}")
     if n <= 8192:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
