@@ -2,13 +2,13 @@
 import torch
 
 from .distributions import MultivariateNormal
-from .likelihoods import GaussianLikelihood
+from .likelihoods import _GaussianLikelihoodBase
 from .module import Module
 
 
 class ExactMarginalLogLikelihood(Module):
     def __init__(self, likelihood, model):
-        if not isinstance(likelihood, GaussianLikelihood):
+        if not isinstance(likelihood, _GaussianLikelihoodBase):
             raise RuntimeError("Likelihood must be Gaussian for exact inference")
         super().__init__()
         self.likelihood = likelihood

@@ -4,7 +4,7 @@ import torch
 
 from . import settings
 from .distributions import MultivariateNormal
-from .likelihoods import GaussianLikelihood
+from .likelihoods import _GaussianLikelihoodBase
 from .module import Module
 
 
@@ -12,7 +12,7 @@ class ExactGP(Module):
     def __init__(self, train_inputs, train_targets, likelihood):
         if train_inputs is not None and torch.is_tensor(train_inputs):
             train_inputs = (train_inputs,)
-        if not isinstance(likelihood, GaussianLikelihood):
+        if not isinstance(likelihood, _GaussianLikelihoodBase):
             raise RuntimeError("ExactGP can only handle Gaussian likelihoods")
         super().__init__()
         self.train_inputs = None if train_inputs is None else tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in train_inputs)

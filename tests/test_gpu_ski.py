@@ -34,7 +34,7 @@ def test_ski_matmul_matches_oracle(cuda_dev, d, sizes, kind):
     axes, lo, step = _grid(sizes, bounds)
     x = torch.rand(n, d, generator=g)
     # points inside the first / last grid cell (one-hot snapping, interpolation.py:84-131) and exactly on nodes
-    x[:20] = torch.rand(20, d, generator=g) * torch.tensor(step) - torch.tensor(step)            # first cell: [lo, lo + step)
+    x[:20] = torch.tensor(lo) + torch.rand(20, d, generator=g) * torch.tensor(step) * 0.999     # first cell: [lo, lo + spacing)
     x[20:40] = torch.tensor([float(a[-1]) for a in axes]) - torch.rand(20, d, generator=g) * torch.tensor(step) * 0.999
     x[40] = torch.tensor([float(a[3]) for a in axes])
     v = torch.randn(n, t, generator=g)
@@ -68,7 +68,7 @@ def test_ski_mll_matches_oracle_and_api(cuda_dev):
     then the same through ScaleKernel(GridInterpolationKernel(RBFKernel())) + ExactMarginalLogLikelihood."""
     from gpytorch_b200.engine import Plan
 
-    n, d, sizes, ls, osc, nz = 2500, 2, [30, 30], 0.25, 1.4, 0.05
+    n, d, sizes, ls, osc, nz = 2500, 2, [30, 30], 0.25, 1.4, 0.3
     x, y = om.synthetic_problem(n, d, 5, torch.float32)
     axes, lo, step = _grid(sizes, [(0.0, 1.0)] * d)
     Kd = ski.ski_matmul("rbf", x.double(), [a.double() for a in axes], ls, osc, torch.eye(n, dtype=torch.float64))
