@@ -29,8 +29,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line; NCCL's own log (whatever NCCL_DEBUG level the caller chose) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries print to fd 1 behind Python's back (NCCL's version banner under
+# NCCL_DEBUG=VERSION/INFO, torchrun notices), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the
+# saved original stdout; NCCL_DEBUG is left as the caller set it.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 WORKLOADS = {
     # BASELINE.json configs[0]: the reference's own CPU-runnable case (N < min_preconditioning_size: no preconditioner,
@@ -233,8 +241,8 @@ def run_reference(args, w):
         return
     cores = tune_threads(w)
     if not dense_fits(w):
-        print(json.dumps({"impl": "reference", "unavailable": f"dense K at N={w['n']} does not fit in this host's memory; "
-                          "the reference's default path materialises K (lazy_evaluated_kernel_tensor.py:343-373)"}), flush=True)
+        emit({"impl": "reference", "unavailable": f"dense K at N={w['n']} does not fit in this host's memory; "
+              "the reference's default path materialises K (lazy_evaluated_kernel_tensor.py:343-373)"})
         return
     # every step is ONE evaluation at the full configuration (never a scaled sample).  The requested warm-up / step counts
     # are honoured as long as the run stays within ~5 minutes; beyond that warm-up, then steps, are cut and the line says so.
@@ -263,7 +271,7 @@ def run_reference(args, w):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -457,7 +465,7 @@ def run_c4(args, w):
                    "mll_per_element": [float(v) for v in out.tolist()]},
         "clocks": clocks, "e2e": None, "gpu_launches": None, "roofline": None, "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, w):
@@ -592,7 +600,7 @@ def run_ours(args, w):
             "clocks": m["clocks"], "e2e": e2e, "gpu_launches": m["launches"], "roofline": m["roofline"], "cpu_baseline": cpu,
             "parity_at_config": parity, "c3": c3,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         comm.close()
