@@ -349,7 +349,7 @@ def measure_workload(w, args, env, steps, warmup, sample_clocks=False):
     trans = (2 if w["kind"] != "rbf" else 1) * rc * n  # transcendental ops per launch (ex2, + sqrt for Matern)
     mufu_peak = 16.0 * info["n_sm"] * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6  # 16 MUFU/clk/SM (tools/mufu_bench.cu: 15.99)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "kmv_tc_dram_bytes.json")
+    tpath = os.path.join(ROOT, "profiles", "kmv_tc2_dram_bytes.json")
     if os.path.exists(tpath) and world == 1 and w is WORKLOADS["c2"] and info["backend"] == "tcgen05":
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
@@ -366,7 +366,7 @@ def measure_workload(w, args, env, steps, warmup, sample_clocks=False):
                 "info": info, "res": res, "flops": 0.0, "kms": kms,
                 "ctx": dict(plan=plan, x=x, y=y, xd=xd, y_loc=y_loc, e1d=e1d, e2d=e2d, radd=radd, rb=rb, rc=rc, l2_flush=l2_flush, barrier=barrier)}
     roofline = {
-        "bound": "tensor", "kernel": info.get("kernel", "gp::kmv_tc_kernel" if info["backend"] == "tcgen05" else "gp::kmv_simt_kernel"),
+        "bound": "tensor", "kernel": info.get("kernel", "gp::v2::kmv_tc2_kernel" if info["backend"] == "tcgen05" else "gp::kmv_simt_kernel"),
         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
         "peak_source": f"bf16 dense burst, {peak_src}; the kernel runs kind::tf32 (nominal half of bf16) with a 3xTF32 split",
         "ms_per_launch": kms, "algorithmic_flops_per_launch": flops,

@@ -427,37 +427,45 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
   }
 }
 
-// W[r][:] = C^{-1} (s_r L[:, r])  (W = L C^{-T}, rows scaled by s_r = 1 / d_r for a per-row noise diagonal): one thread per row runs
-// the forward substitution against C (fp64, shared memory, broadcast reads) with its partial results w_b in shared memory (fp32,
-// [b][thread]: conflict free); four independent partial sums break the dependent FMA chain.  Replaces the explicit inverse
-// C^{-1} + dense [k x k] . [k x n] product of round 1 (0.16 + 0.19 ms at C2).
-constexpr int WS_THREADS = 128;
-__global__ void __launch_bounds__(WS_THREADS)
-wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
-              const double* __restrict__ C, const float* __restrict__ dvec, float* __restrict__ W) {
-  extern __shared__ double shw[];
-  double* Cs = shw;                                             // [k][k] lower triangle of C
-  float* wcol = reinterpret_cast<float*>(shw + (size_t)k * k);  // [k][WS_THREADS]
-  for (int e = threadIdx.x; e < k * k; e += WS_THREADS) Cs[e] = C[e];
+// Cinv = C^{-1} (lower triangular, fp64): one thread per column, forward substitution against C in shared memory
+__global__ void cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
+  extern __shared__ double Is[];  // [k][k] C^{-1}, built column by column in shared memory (C itself: broadcast loads, L1)
+  const int j = threadIdx.x;
+  if (j < k) {
+    for (int i = 0; i < k; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int b = j; b < i; ++b) s -= __ldg(C + i * k + b) * Is[b * k + j];
+      Is[i * k + j] = (i < j) ? 0.0 : s / __ldg(C + i * k + i);
+    }
+  }
   __syncthreads();
-  const int tid = threadIdx.x;
-  for (int64_t r = (int64_t)blockIdx.x * WS_THREADS + tid; r < n_local; r += (int64_t)gridDim.x * WS_THREADS) {
-    const int64_t gr = row_begin + r;
-    const double sc = dvec ? 1.0 / (double)dvec[gr] : 1.0;
-    for (int a = 0; a < k; ++a) {
-      double s0 = sc * (double)Lt[(int64_t)a * n_total + gr], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* ca = Cs + (size_t)a * k;
-      int b = 0;
-      for (; b + 4 <= a; b += 4) {
-        s0 = fma(-ca[b], (double)wcol[b * WS_THREADS + tid], s0);
-        s1 = fma(-ca[b + 1], (double)wcol[(b + 1) * WS_THREADS + tid], s1);
-        s2 = fma(-ca[b + 2], (double)wcol[(b + 2) * WS_THREADS + tid], s2);
-        s3 = fma(-ca[b + 3], (double)wcol[(b + 3) * WS_THREADS + tid], s3);
-      }
-      for (; b < a; ++b) s0 = fma(-ca[b], (double)wcol[b * WS_THREADS + tid], s0);
-      const float w = (float)(((s0 + s1) + (s2 + s3)) / ca[a]);
-      wcol[a * WS_THREADS + tid] = w;
-      W[r * k + a] = w;
+  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cinv[e] = Is[e];
+}
+
+constexpr int WS_BLOCKS = 4;
+// W[r][a] = sum_{b<=a} Cinv[a][b] L[b][r]   (W = L C^{-T}); 32 rows x 4 interleaved a-groups per pass, fp64 accumulate
+__global__ void __launch_bounds__(128)
+wsolve_kernel(const float* __restrict__ Lt, int k, int64_t n_total, int64_t row_begin, int64_t n_local,
+              const double* __restrict__ Cinv, const float* __restrict__ dvec, float* __restrict__ W) {
+  extern __shared__ double shw[];
+  double* Ci = shw;                        // [k][k]
+  double* Ls = shw + (size_t)k * k;        // [k][32], fp64 copy of the L rows (exact conversion, once per element)
+  for (int e = threadIdx.x; e < k * k; e += 128) Ci[e] = Cinv[e];
+  const int rl = threadIdx.x & 31, ag = threadIdx.x >> 5;
+  for (int blk = 0; blk < WS_BLOCKS; ++blk) {          // C^{-1} (80 KB at k = 100) is loaded once per WS_BLOCKS * 32 rows
+    const int64_t r0 = ((int64_t)blockIdx.x * WS_BLOCKS + blk) * 32;
+    if (r0 >= n_local) break;
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * 32; e += 128) {
+      int b = e >> 5, rr = e & 31;
+      Ls[e] = (r0 + rr < n_local) ? (double)Lt[(int64_t)b * n_total + row_begin + r0 + rr] : 0.0;
+    }
+    __syncthreads();
+    const int64_t r = r0 + rl;
+    for (int a = ag; a < k; a += 4) {
+      double s = 0.0;
+      for (int b = 0; b <= a; ++b) s = fma(Ci[a * k + b], Ls[b * 32 + rl], s);
+      if (r < n_local) W[r * k + a] = (float)(dvec ? s / (double)dvec[row_begin + r] : s);   // per-row noise: W = D^-1 L C^-T
     }
   }
 }
@@ -582,9 +590,10 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
   const int nz = (int)std::min<int64_t>(64, std::max<int64_t>(1, std::min<int64_t>(n / 1024, (2 * p->n_sm) / (ntile * (ntile + 1) / 2))));
   const int64_t jslice = cdiv(cdiv(n, nz), 64) * 64;
   GP_CHECK(p->gram.ensure(sizeof(double) * (size_t)nz * k * k));
-  GP_CHECK(p->cholC.ensure(sizeof(double) * ((size_t)k * k + 4) + 64));
+  GP_CHECK(p->cholC.ensure(sizeof(double) * ((size_t)2 * k * k + 4) + 64));
   double* C = p->cholC.as<double>();
-  double* d_logdet = C + (size_t)k * k;
+  double* Cinv = C + (size_t)k * k;
+  double* d_logdet = Cinv + (size_t)k * k;
   double* d_tail = d_logdet + 1;
   int* d_fail = reinterpret_cast<int*>(d_tail + 1);
   GP_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
@@ -598,17 +607,20 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
     GP_CUDA(cudaMemcpyAsync(d_tail, &tail, sizeof(double), cudaMemcpyHostToDevice, st));   // pageable source: copied before return
   }
   const size_t shc = sizeof(double) * (size_t)k * k;
-  const size_t shw = shc + sizeof(float) * (size_t)k * WS_THREADS;
   static bool attr_done[64] = {};
   if (!attr_done[p->device & 63]) {
     GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // k <= 128: 128 KB
-    GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       // 128 KB + 64 KB
+    GP_CUDA(cudaFuncSetAttribute(cinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));       // 128 KB + 32 KB
     attr_done[p->device & 63] = true;
   }
   chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, dvec ? 1.0 : (double)p->noise, d_tail, C, d_logdet, d_fail);
-  wsolve_kernel<<<(unsigned)std::min<int64_t>(cdiv(p->row_count, WS_THREADS), 4 * p->n_sm), WS_THREADS, shw, st>>>(
-      Lt, k, n, p->row_begin, p->row_count, C, dvec, W);
-  p->launches += 3;
+  // W = L C^-T through the explicit inverse (a per-row forward substitution against C in shared memory was tried: 0.52 ms at C2
+  // against 0.16 + 0.19 ms for these two kernels -- one 128-thread CTA per SM is latency bound on 5000 dependent steps per row)
+  cinv_kernel<<<1, 128, shc, st>>>(C, k, Cinv);
+  wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32 * WS_BLOCKS), 128, shc + sizeof(double) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin,
+                                                                                                      p->row_count, Cinv, dvec, W);
+  p->launches += 4;
   GP_CUDA(cudaGetLastError());
   double* h = reinterpret_cast<double*>(reinterpret_cast<char*>(p->pinned) + 3072);
   GP_CUDA(cudaMemcpyAsync(h, d_logdet, sizeof(double) * 2 + sizeof(int), cudaMemcpyDeviceToHost, st));
