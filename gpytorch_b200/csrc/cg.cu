@@ -62,20 +62,30 @@ __device__ __forceinline__ void block_reduce_cols(float4 acc, float* red /*[CG_R
 }
 
 // sum G partial vectors of length L (fp32) into fp64, fixed order.  Block = 32 outputs x 8 partial groups.
-__global__ void cg_sum_kernel(const float* __restrict__ in, int G, int L, double* __restrict__ out, const int* done) {
+constexpr int SUM_GROUPS = 32;  // cg_sum_kernel: 32 outputs x 32 row groups per CTA
+__global__ void __launch_bounds__(32 * SUM_GROUPS) cg_sum_kernel(const float* __restrict__ in, int G, int L, double* __restrict__ out,
+                                                                  const int* done) {
   if (done && *done) return;
-  __shared__ double sh[8][33];
+  __shared__ double sh[SUM_GROUPS][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int o = blockIdx.x * 32 + lane;
   double s = 0.0;
-  if (o < L)
-    for (int b = grp; b < G; b += 8) s += (double)in[(size_t)b * L + o];
+  if (o < L) {
+    // independent loads first (the partial matrix is [G][L]: one 128-byte line per row and warp), fixed summation order
+    int b = grp;
+    for (; b + 3 * SUM_GROUPS < G; b += 4 * SUM_GROUPS) {
+      const float v0 = in[(size_t)b * L + o], v1 = in[(size_t)(b + SUM_GROUPS) * L + o];
+      const float v2 = in[(size_t)(b + 2 * SUM_GROUPS) * L + o], v3 = in[(size_t)(b + 3 * SUM_GROUPS) * L + o];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < G; b += SUM_GROUPS) s += (double)in[(size_t)b * L + o];
+  }
   sh[grp][lane] = s;
   __syncthreads();
   if (grp == 0 && o < L) {
     double t = 0.0;
 #pragma unroll
-    for (int g2 = 0; g2 < 8; ++g2) t += sh[g2][lane];
+    for (int g2 = 0; g2 < SUM_GROUPS; ++g2) t += sh[g2][lane];
     out[o] = t;
   }
 }
@@ -570,7 +580,8 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   const bool precond = W != nullptr;
   if (!precond) k = 0;
   const int wp = precond ? w_pitch(k) : 0;
-  const int G = (int)std::min<int64_t>(cdiv(n, CG_ROWS), 2 * p->n_sm);
+  static const int grid_mult = getenv("GP_CG_GRID_MULT") ? std::max(1, atoi(getenv("GP_CG_GRID_MULT"))) : 2;   // CTAs per SM of the row-pass kernels
+  const int G = (int)std::min<int64_t>(cdiv(n, CG_ROWS), (int64_t)grid_mult * p->n_sm);
   const int L1 = TP + k * TP;           // message 1: pV | W^T V
   const float* dvec = p->noise_diag ? p->noise_diag + p->row_begin : nullptr;
   GP_REQUIRE(!precond || dvec != nullptr || p->noise > 0.f, GP_E_SHAPE, "the preconditioner needs noise > 0");
@@ -625,20 +636,20 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
 
   // ---- init: normalise rhs, R, U ; w = W^T R ; Z = P^-1 R ; P = Z ; gamma = z.r ----
   cg_rhs_sq_kernel<<<G, CG_THREADS, 0, st>>>(RHS, ldr, t, n, red1);
-  cg_sum_kernel<<<1, 256, 0, st>>>(red1, G, TP, sums0, nullptr);
+  cg_sum_kernel<<<1, 32 * SUM_GROUPS, 0, st>>>(red1, G, TP, sums0, nullptr);
   GP_CHECK(allreduce(p, sums0, TP));
   cg_init_kernel<<<G, CG_THREADS, 0, st>>>(RHS, ldr, t, n, sums0, eps, U, R, S);
   p->launches += 3;
   if (precond) {
     cg_finishv_wtv_kernel<false><<<G, CG_THREADS, sh_b, st>>>(nullptr, 0, 0, 0.f, 0.f, nullptr, nullptr, nullptr, R, W, k, wp, n, red1, L1,
                                                            nullptr, p->xbad);
-    cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 256, 0, st>>>(red1, G, L1, sums1, nullptr);
+    cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 32 * SUM_GROUPS, 0, st>>>(red1, G, L1, sums1, nullptr);
     GP_CHECK(allreduce(p, sums1, L1));
     p->launches += 2;
   }
   cg_update_precond_kernel<true><<<G, CG_THREADS, sh_d, st>>>(sums1, 0, eps, nullptr, nullptr, U, R, Z, W, k, wp, nullptr, inv_noise, dvec, n, S,
                                                              red2, L2);
-  cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 256, 0, st>>>(red2, G, L2, sums2, nullptr);
+  cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 32 * SUM_GROUPS, 0, st>>>(red2, G, L2, sums2, nullptr);
   GP_CHECK(allreduce(p, sums2, L2));
   cg_dir_pack_kernel<true><<<Gd, CG_THREADS, 0, st>>>(sums2, 0, eps, stop_after, tol, t, n_tridiag, n_tridiag_iter, max_iter, Z, P, n,
                                                      nchunk_pack, Vt, S, TMAT, max_tridiag_iter);
@@ -658,12 +669,12 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
     if ((status = kmv()) != GP_OK) break;
     cg_finishv_wtv_kernel<true><<<G, CG_THREADS, sh_b, st>>>(p->partial.as<float>(), p->nparts, p->rows_pad, p->outputscale, p->noise, dvec, P, V,
                                                           nullptr, W, k, wp, n, red1, L1, done, p->xbad);
-    cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 256, 0, st>>>(red1, G, L1, sums1, done);
+    cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 32 * SUM_GROUPS, 0, st>>>(red1, G, L1, sums1, done);
     if ((status = allreduce(p, sums1, L1)) != GP_OK) break;
     // w_kk = W^T R_kk: the direct product shipped in message 2 of the previous launch of this kernel (start-up pass for kk = 0)
     cg_update_precond_kernel<false><<<G, CG_THREADS, sh_d, st>>>(sums1, kk, eps, P, V, U, R, Z, W, k, wp, sums2 + 2 * TP, inv_noise, dvec, n, S,
                                                                 red2, L2);
-    cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 256, 0, st>>>(red2, G, L2, sums2, done);
+    cg_sum_kernel<<<(unsigned)cdiv(L2, 32), 32 * SUM_GROUPS, 0, st>>>(red2, G, L2, sums2, done);
     if ((status = allreduce(p, sums2, L2)) != GP_OK) break;
     cg_dir_pack_kernel<false><<<Gd, CG_THREADS, 0, st>>>(sums2, kk, eps, stop_after, tol, t, n_tridiag, n_tridiag_iter, max_iter, Z, P, n,
                                                         nchunk_pack, Vt, S, TMAT, max_tridiag_iter);

@@ -142,7 +142,7 @@ struct gp_plan {
   int* xbad = nullptr;  // device flag: non-finite value in the packed inputs (lives behind mean[])
   gp::DevBuf mean, scale, Z1, Z2, XA, XB, V16, Vtiles, partial, out16;
   gp::DevBuf cgU, cgR, cgZ, cgP, cgV, cgPfull, red, sums, qtr, state, tmat_tmp, misc, misc2, misc3;
-  gp::DevBuf pcdiag, pcperm, pcpos, pcstate, gram, cholC;
+  gp::DevBuf pcdiag, pcperm, pcpos, pcstate, pcpart, gram, cholC;
   gp_comm* comm = nullptr;
   gp_ski_state* ski = nullptr;   // non-null: backend == GP_BACKEND_SKI
   void* pinned = nullptr;  // small pinned host scratch

@@ -305,6 +305,164 @@ pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, i
   }
 }
 
+// Single-barrier form of the persistent kernel.  Every CTA reduces the per-CTA partials itself (same loads, same tree => the
+// same pivot, error and stop decision everywhere), so the second grid barrier of pc_persistent_kernel ("state published") is
+// not needed: nothing global is read back except the partials, which are double-buffered by step parity (a CTA can only
+// overwrite buffer m & 1 at step m + 2, i.e. after barrier m + 1, which every CTA reaches after it has read the step-m
+// partials).  The permutation is not materialised: a row's position is private to the thread that owns the row (pos[j],
+// patched by the owner when the row is swapped), the winning partial carries its row index, and the row that sits at
+// position m + 1 (the one the swap moves to the winner's old position) announces itself through one more partial.
+// Arithmetic, tie-breaking (earliest position) and reduction order are those of pc_persistent_kernel: bit-identical pivots.
+struct PcPart {
+  double sum;
+  float val;
+  int pos, idx, old;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(PCP_THREADS)
+pc_persistent1_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, int64_t n, int max_rank, float tol,
+                      float* diag, int* pos, PcState* st, int64_t* piv_out, PcPart* part) {
+  extern __shared__ float sh[];
+  float* zp = sh;
+  float* lp = sh + DP;
+  float* col = lp + max_rank;
+  __shared__ float s_val[PCP_RED];
+  __shared__ int s_pos[PCP_RED];
+  __shared__ int s_idx[PCP_RED];
+  __shared__ double s_sum[PCP_RED];
+  __shared__ int s_old;
+  const int tid = threadIdx.x;
+  const int G = (int)gridDim.x;
+  if (tid < PCP_RED - PCP_THREADS) {
+    s_val[PCP_THREADS + tid] = -INFINITY; s_pos[PCP_THREADS + tid] = 0x7fffffff; s_idx[PCP_THREADS + tid] = -1; s_sum[PCP_THREADS + tid] = 0.0;
+  }
+  const int64_t stride = (int64_t)G * PCP_THREADS;
+  const int64_t jfirst = (int64_t)blockIdx.x * PCP_THREADS + tid;
+  // CTA-uniform running state (identical in every CTA)
+  int pi = st->pivot;                 // pivot row of the step about to run (position m)
+  float dpiv = st->dpiv;
+  const float orig_err = st->orig_err;
+  int fx_new = -1, fx_old = -1, fx_pp = 0;   // pending position patches from the previous selection
+  auto better = [](float v2, int p2, float v1, int p1) { return v2 > v1 || (v2 == v1 && p2 < p1); };
+  for (int m = 0; m < max_rank; ++m) {
+    if (tid == 0) s_old = -1;
+    for (int c = tid; c < DP; c += PCP_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+    for (int q = tid; q < m; q += PCP_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM, before the last barrier
+    __syncthreads();
+    float best = -INFINITY;
+    int best_pos = 0x7fffffff, best_idx = -1;
+    double asum = 0.0;
+    float* Lm = Lt + (int64_t)m * n;
+    for (int64_t j = jfirst; j < n; j += stride) {
+      int pj = pos[j];                                   // owner-private
+      if ((int)j == fx_new) { pj = m; pos[j] = m; }      // pos[pi_new] = m (this step's pivot)
+      else if ((int)j == fx_old) { pj = fx_pp; pos[j] = fx_pp; }
+      if (pj == m + 1) s_old = (int)j;                   // exactly one thread of the grid
+      const bool cached = (j == jfirst);
+      if (pj < m) {
+        Lm[j] = 0.f;
+        if (cached) col[m * PCP_THREADS + tid] = 0.f;
+      } else if (pj == m) {
+        Lm[j] = dpiv;
+        if (cached) col[m * PCP_THREADS + tid] = dpiv;
+      } else {
+        float s = 0.f;
+        for (int c = 0; c < DP; ++c) {
+          float df = zp[c] - Z[j * DP + c];
+          s = fmaf(df, df, s);
+        }
+        float v = os * cov_from_arg<KIND>(-0.5f * s);
+        {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int q = 0;
+          if (cached) {
+            const float* cj = col + tid;
+            for (; q + 4 <= m; q += 4) {
+              s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
+              s1 = fmaf(lp[q + 1], cj[(q + 1) * PCP_THREADS], s1);
+              s2 = fmaf(lp[q + 2], cj[(q + 2) * PCP_THREADS], s2);
+              s3 = fmaf(lp[q + 3], cj[(q + 3) * PCP_THREADS], s3);
+            }
+            for (; q < m; ++q) s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
+          } else {
+            for (; q + 4 <= m; q += 4) {
+              s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
+              s1 = fmaf(lp[q + 1], Lt[(int64_t)(q + 1) * n + j], s1);
+              s2 = fmaf(lp[q + 2], Lt[(int64_t)(q + 2) * n + j], s2);
+              s3 = fmaf(lp[q + 3], Lt[(int64_t)(q + 3) * n + j], s3);
+            }
+            for (; q < m; ++q) s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
+          }
+          v -= (s0 + s1) + (s2 + s3);
+        }
+        v /= dpiv;
+        Lm[j] = v;
+        if (cached) col[m * PCP_THREADS + tid] = v;
+        const float dn = diag[j] - v * v;
+        diag[j] = dn;
+        float cv; int cp;
+        if (dn != dn) { cv = INFINITY; cp = -1; }
+        else { cv = dn; cp = pj; }
+        if (better(cv, cp, best, best_pos)) { best = cv; best_pos = cp; best_idx = (int)j; }
+        asum += fabs((double)dn);
+      }
+    }
+    s_val[tid] = best; s_pos[tid] = best_pos; s_idx[tid] = best_idx; s_sum[tid] = asum;
+    __syncthreads();
+    for (int s = PCP_RED / 2; s > 0; s >>= 1) {
+      if (tid < s && tid + s < PCP_RED) {
+        if (better(s_val[tid + s], s_pos[tid + s], s_val[tid], s_pos[tid])) { s_val[tid] = s_val[tid + s]; s_pos[tid] = s_pos[tid + s]; s_idx[tid] = s_idx[tid + s]; }
+        s_sum[tid] += s_sum[tid + s];
+      }
+      __syncthreads();
+    }
+    PcPart* mine = part + (size_t)(m & 1) * G;
+    if (tid == 0) {
+      PcPart pp; pp.sum = s_sum[0]; pp.val = s_val[0]; pp.pos = s_pos[0]; pp.idx = s_idx[0]; pp.old = s_old;
+      mine[blockIdx.x] = pp;
+    }
+    pc_grid_barrier(&st->bar, (unsigned)(m + 1) * gridDim.x);   // all partials of step m are visible
+    best = -INFINITY; best_pos = 0x7fffffff; best_idx = -1; asum = 0.0;
+    int old = -1;
+    for (int b = tid; b < G; b += PCP_THREADS) {   // fixed assignment + fixed tree => deterministic, identical in every CTA
+      const PcPart* q = mine + b;
+      const float v2 = __ldcg(&q->val); const int p2 = __ldcg(&q->pos);
+      if (better(v2, p2, best, best_pos)) { best = v2; best_pos = p2; best_idx = __ldcg(&q->idx); }
+      asum += __ldcg(&q->sum);
+      old = max(old, __ldcg(&q->old));
+    }
+    s_val[tid] = best; s_pos[tid] = best_pos; s_idx[tid] = best_idx; s_sum[tid] = asum;
+    if (old >= 0) s_old = old;     // at most one thread of the CTA (after the loop barrier below: s_old is re-read only then)
+    __syncthreads();
+    for (int s = PCP_RED / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+        if (better(s_val[tid + s], s_pos[tid + s], s_val[tid], s_pos[tid])) { s_val[tid] = s_val[tid + s]; s_pos[tid] = s_pos[tid + s]; s_idx[tid] = s_idx[tid + s]; }
+        s_sum[tid] += s_sum[tid + s];
+      }
+      __syncthreads();
+    }
+    const double tot = s_sum[0];
+    const float err = (float)(tot / (double)orig_err);
+    const float mx = s_val[0];
+    const int ppw = s_pos[0], inew = s_idx[0], iold = s_old;
+    bool stop = false, nan = false;
+    if (m + 1 >= max_rank || (int64_t)(m + 1) >= n || !(err > tol)) stop = true;
+    else if (ppw < 0 || !(mx > 0.f)) { stop = true; nan = true; }
+    if (blockIdx.x == 0 && tid == 0) {
+      st->rank = m + 1;
+      st->err = err;
+      if (stop) st->done = 1;
+      if (nan) st->nan_flag = 1;
+      if (!stop) { st->pivot = inew; st->dpiv = sqrtf(mx); piv_out[m + 1] = (int64_t)inew; }
+    }
+    if (stop) break;
+    pi = inew; dpiv = sqrtf(mx);
+    fx_new = inew; fx_old = (iold == inew) ? -1 : iold; fx_pp = ppw;
+    __syncthreads();   // s_val / s_old are rewritten at the top of the next step
+  }
+}
+
 __global__ void pc_init_kernel(float* __restrict__ diag, int* __restrict__ perm, int* __restrict__ pos, int64_t n, float os,
                                PcState* __restrict__ st, int64_t* __restrict__ piv_out) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,45 +559,53 @@ __global__ void chol_small_kernel(const double* __restrict__ Gpart, int nz, int 
     G[e] = s;
   }
   __syncthreads();
+  // Right-looking factorisation with ONE barrier per step: the scaled column j goes straight to the output (nobody reads it
+  // back), the trailing update uses the unscaled column and 1 / d_jj:  G[i][l] -= G[i][j] G[l][j] / d_jj.
+  double ld = 0.0;
   for (int j = 0; j < k; ++j) {
-    if (tid == 0) {
-      double d = G[j * k + j];
-      if (!(d > 0.0)) { *fail = 1; d = 1e-300; }
-      G[j * k + j] = sqrt(d);
+    double d = G[j * k + j];
+    if (!(d > 0.0)) { if (tid == 0) *fail = 1; d = 1e-300; }
+    const double rinv = 1.0 / d;
+    if (tid == 0) ld += log(d);
+    if (tid >= 256) {   // upper half of the CTA also writes column j of C (rows j..k-1) and the zeros above the diagonal
+      const double rs = 1.0 / sqrt(d);
+      for (int i = tid - 256; i < k; i += (int)blockDim.x - 256) C[i * k + j] = (i < j) ? 0.0 : G[i * k + j] * rs;
     }
-    __syncthreads();
-    const double djj = G[j * k + j];
-    for (int i = j + 1 + tid; i < k; i += blockDim.x) G[i * k + j] /= djj;
-    __syncthreads();
-    // trailing update: G[i][l] -= G[i][j] G[l][j] for j < l <= i
-    // (2-D thread mapping, no integer division: every (i, l) is still updated exactly once with the same operands)
+    // (2-D thread mapping, no integer division: every (i, l), j < l <= i, is updated exactly once)
     for (int i = j + 1 + (tid >> 5); i < k; i += (int)(blockDim.x >> 5)) {
-      const double gij = G[i * k + j];
+      const double gij = G[i * k + j] * rinv;
       for (int l = j + 1 + (tid & 31); l <= i; l += 32) G[i * k + l] -= gij * G[l * k + j];
     }
     __syncthreads();
   }
-  for (int e = tid; e < k * k; e += blockDim.x) C[e] = (e % k <= e / k) ? G[e] : 0.0;
-  if (tid == 0) {
-    double ld = 0.0;
-    for (int j = 0; j < k; ++j) ld += log(G[j * k + j]);
-    *logdet_out = 2.0 * ld + *logdet_tail;
-  }
+  if (tid == 0) *logdet_out = ld + *logdet_tail;
 }
 
-// Cinv = C^{-1} (lower triangular, fp64): one thread per column, forward substitution against C in shared memory
-__global__ void cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
-  extern __shared__ double Is[];  // [k][k] C^{-1}, built column by column in shared memory (C itself: broadcast loads, L1)
-  const int j = threadIdx.x;
-  if (j < k) {
-    for (int i = 0; i < k; ++i) {
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int b = j; b < i; ++b) s -= __ldg(C + i * k + b) * Is[b * k + j];
-      Is[i * k + j] = (i < j) ? 0.0 : s / __ldg(C + i * k + i);
+// Cinv = C^{-1} (lower triangular, fp64): one WARP (= one CTA) per column j, forward substitution with the column held in
+// registers (entry b on lane b & 31) and the inner product of step i split over the lanes + a shuffle tree: ~100 dependent
+// steps of ~150 cycles instead of 5000 dependent FMAs of one thread per column.  k <= 128.
+__global__ void __launch_bounds__(32) cinv_kernel(const double* __restrict__ C, int k, double* __restrict__ Cinv) {
+  const int j = blockIdx.x, lane = threadIdx.x;
+  double x[4] = {0.0, 0.0, 0.0, 0.0};   // x[t] = Cinv[lane + 32 t][j]
+  for (int i = 0; i < k; ++i) {
+    double xi = 0.0;
+    if (i >= j) {
+      const double* ci = C + (size_t)i * k;
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int b = lane + 32 * t;
+        if (b >= j && b < i) s = fma(ci[b], x[t], s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      xi = (((i == j) ? 1.0 : 0.0) - s) / ci[i];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t == i) x[t] = xi;
     }
+    if (lane == 0) Cinv[(size_t)i * k + j] = xi;
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < k * k; e += blockDim.x) Cinv[e] = Is[e];
 }
 
 constexpr int WS_BLOCKS = 4;
@@ -550,8 +716,27 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
     int DPv = p->DP, rk = rank;
     float osv = p->outputscale, tolv = error_tol;
     int64_t nn = n;
-    void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &perm, &pos, &S, &piv, &pval, &ppos, &psum};
-    GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PCP_THREADS), args, sh, st));
+    if (getenv("GP_PC_TWOBAR") != nullptr) {   // A-B switch: the two-barrier form (CTA 0 reduces, second barrier publishes)
+      void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &perm, &pos, &S, &piv, &pval, &ppos, &psum};
+      GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PCP_THREADS), args, sh, st));
+    } else {
+      const void* fn1;
+      switch (p->kind) {
+        case GP_RBF: fn1 = (const void*)pc_persistent1_kernel<GP_RBF>; break;
+        case GP_MATERN12: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN12>; break;
+        case GP_MATERN32: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN32>; break;
+        default: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN52>; break;
+      }
+      GP_CUDA(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      int per_sm1 = 0;
+      GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn1, PCP_THREADS, sh));
+      GP_REQUIRE(per_sm1 >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
+      const unsigned grid1 = (unsigned)std::min<int64_t>(cdiv(n, PCP_THREADS), (int64_t)per_sm1 * p->n_sm);
+      GP_CHECK(p->pcpart.ensure(sizeof(PcPart) * 2 * (size_t)grid1));
+      PcPart* part = p->pcpart.as<PcPart>();
+      void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &pos, &S, &piv, &part};
+      GP_CUDA(cudaLaunchCooperativeKernel(fn1, dim3(grid1), dim3(PCP_THREADS), args, sh, st));
+    }
     p->launches += 1;
   } else {
   for (int m = 0; m < rank; ++m) {
@@ -610,14 +795,13 @@ extern "C" int gp_precond_build(gp_plan* p, const float* Lt, int k, float* W, do
   static bool attr_done[64] = {};
   if (!attr_done[p->device & 63]) {
     GP_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // k <= 128: 128 KB
-    GP_CUDA(cudaFuncSetAttribute(cinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     GP_CUDA(cudaFuncSetAttribute(wsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024));       // 128 KB + 32 KB
     attr_done[p->device & 63] = true;
   }
   chol_small_kernel<<<1, 512, shc, st>>>(p->gram.as<double>(), nz, k, dvec ? 1.0 : (double)p->noise, d_tail, C, d_logdet, d_fail);
   // W = L C^-T through the explicit inverse (a per-row forward substitution against C in shared memory was tried: 0.52 ms at C2
   // against 0.16 + 0.19 ms for these two kernels -- one 128-thread CTA per SM is latency bound on 5000 dependent steps per row)
-  cinv_kernel<<<1, 128, shc, st>>>(C, k, Cinv);
+  cinv_kernel<<<k, 32, 0, st>>>(C, k, Cinv);
   wsolve_kernel<<<(unsigned)cdiv(p->row_count, 32 * WS_BLOCKS), 128, shc + sizeof(double) * (size_t)k * 32, st>>>(Lt, k, n, p->row_begin,
                                                                                                       p->row_count, Cinv, dvec, W);
   p->launches += 4;
