@@ -166,7 +166,7 @@ __device__ __forceinline__ void stage_w(const float* __restrict__ W, int k, int 
 // out: part[blockIdx][0..16) = sum p.V (FINISH only) ; part[blockIdx][16 + kk*16 + c] = sum_r W[r][kk] X[r][c]
 template <bool FINISH>
 __global__ void __launch_bounds__(CG_THREADS)
-cg_finishv_wtv_kernel(const float* __restrict__ kpart, int nsplit, int64_t rows_pad, float os, float noise,
+cg_finishv_wtv_kernel(const float* __restrict__ kpart, int nsplit, int64_t rows_pad, float os, const float* __restrict__ pscale, float noise,
                       const float* __restrict__ dvec, const float* __restrict__ P, float* __restrict__ V,
                       const float* __restrict__ Xin, const float* __restrict__ W, int k, int wp, int64_t n,
                       float* __restrict__ part, int L, const int* done, const int* __restrict__ xbad) {
@@ -198,13 +198,23 @@ cg_finishv_wtv_kernel(const float* __restrict__ kpart, int nsplit, int64_t rows_
       if (rl < nr) {
         if (FINISH) {
           float4 s = make_float4(poison, poison, poison, poison);
-          for (int sp = 0; sp < nsplit; ++sp) {
-            const float4 a = reinterpret_cast<const float4*>(kpart)[((int64_t)sp * rows_pad + r) * 4 + cg];
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+          float osr = os;
+          if (pscale) {   // kernel sum: slot sp belongs to the term with outputscale pscale[sp]
+            for (int sp = 0; sp < nsplit; ++sp) {
+              const float4 a = reinterpret_cast<const float4*>(kpart)[((int64_t)sp * rows_pad + r) * 4 + cg];
+              const float w = pscale[sp];
+              s.x = fmaf(w, a.x, s.x); s.y = fmaf(w, a.y, s.y); s.z = fmaf(w, a.z, s.z); s.w = fmaf(w, a.w, s.w);
+            }
+            osr = 1.f;
+          } else {
+            for (int sp = 0; sp < nsplit; ++sp) {
+              const float4 a = reinterpret_cast<const float4*>(kpart)[((int64_t)sp * rows_pad + r) * 4 + cg];
+              s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            }
           }
           const float4 p = reinterpret_cast<const float4*>(P)[r * 4 + cg];
           const float d = dvec ? dvec[r] : noise;
-          x = make_float4(fmaf(d, p.x, os * s.x), fmaf(d, p.y, os * s.y), fmaf(d, p.z, os * s.z), fmaf(d, p.w, os * s.w));
+          x = make_float4(fmaf(d, p.x, osr * s.x), fmaf(d, p.y, osr * s.y), fmaf(d, p.z, osr * s.z), fmaf(d, p.w, osr * s.w));
           reinterpret_cast<float4*>(V)[r * 4 + cg] = x;
           acc.x = fmaf(p.x, x.x, acc.x); acc.y = fmaf(p.y, x.y, acc.y); acc.z = fmaf(p.z, x.z, acc.z); acc.w = fmaf(p.w, x.w, acc.w);
         } else {
@@ -623,7 +633,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
 
   // the direction block is written straight into the packed K.V tiles when this rank owns all rows and the tensor-core
   // kernel runs; sharded runs all-gather the fp32 rows first and pack the gathered block (pack.cu)
-  const bool tc = p->backend == GP_BACKEND_TCGEN05;
+  const bool tc = plan_is_tc(p);
   const bool fuse_pack = tc && !sharded;
   float* Vt = fuse_pack ? p->Vtiles.as<float>() : nullptr;
   const int64_t nchunk_pack = fuse_pack ? p->ntile_j * (TILE_J / 4) : 0;
@@ -641,7 +651,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   cg_init_kernel<<<G, CG_THREADS, 0, st>>>(RHS, ldr, t, n, sums0, eps, U, R, S);
   p->launches += 3;
   if (precond) {
-    cg_finishv_wtv_kernel<false><<<G, CG_THREADS, sh_b, st>>>(nullptr, 0, 0, 0.f, 0.f, nullptr, nullptr, nullptr, R, W, k, wp, n, red1, L1,
+    cg_finishv_wtv_kernel<false><<<G, CG_THREADS, sh_b, st>>>(nullptr, 0, 0, 0.f, nullptr, 0.f, nullptr, nullptr, nullptr, R, W, k, wp, n, red1, L1,
                                                            nullptr, p->xbad);
     cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 32 * SUM_GROUPS, 0, st>>>(red1, G, L1, sums1, nullptr);
     GP_CHECK(allreduce(p, sums1, L1));
@@ -667,7 +677,7 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   bool finished = false;
   for (kk = 0; kk < max_iter && !finished; ++kk) {
     if ((status = kmv()) != GP_OK) break;
-    cg_finishv_wtv_kernel<true><<<G, CG_THREADS, sh_b, st>>>(p->partial.as<float>(), p->nparts, p->rows_pad, p->outputscale, p->noise, dvec, P, V,
+    cg_finishv_wtv_kernel<true><<<G, CG_THREADS, sh_b, st>>>(p->partial.as<float>(), p->nparts, p->rows_pad, p->outputscale, part_scale_ptr(p), p->noise, dvec, P, V,
                                                           nullptr, W, k, wp, n, red1, L1, done, p->xbad);
     cg_sum_kernel<<<(unsigned)cdiv(L1, 32), 32 * SUM_GROUPS, 0, st>>>(red1, G, L1, sums1, done);
     if ((status = allreduce(p, sums1, L1)) != GP_OK) break;

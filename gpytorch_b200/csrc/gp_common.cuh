@@ -145,6 +145,15 @@ struct gp_plan {
   gp::DevBuf pcdiag, pcperm, pcpos, pcstate, pcpart, gram, cholC;
   gp_comm* comm = nullptr;
   gp_ski_state* ski = nullptr;   // non-null: backend == GP_BACKEND_SKI
+  // kernel sums (GP_BACKEND_SUM): the terms (caller-owned plans over the same rows); while the parent launches a term's K.V
+  // kernel the term writes into the parent's partial slots and reads the parent's packed V tiles
+  std::vector<gp_plan*> terms;
+  bool sum_tc = false;            // every term runs the tcgen05 kernel (the direction block is packed once for all of them)
+  bool sum_any_tc = false;        // at least one term reads the packed V tiles
+  float* partial_ext = nullptr;   // set on a TERM for the duration of one launch by its parent
+  float* vtiles_ext = nullptr;
+  gp::DevBuf part_scale;          // [nparts] outputscale of the term that owns each partial slot
+  std::vector<float> part_scale_host;
   void* pinned = nullptr;  // small pinned host scratch
   long long* tc_trace = nullptr;  // optional device buffer [256][8] for the pipeline event trace of CTA (0,0)
 };
@@ -164,6 +173,14 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
 int choose_geometry(gp_plan* p);
 int ski_pack(gp_plan* p);                                               // ski.cu
 int ski_kmv_partials(gp_plan* p, const float* V16, const int* done_flag);
+int sum_pack(gp_plan* p);                                               // sum.cu: geometry / buffers of a kernel-sum plan
+int sum_prepare(gp_plan* p);                                            // refresh the per-slot outputscales (no-op for other plans)
+int sum_kmv_launch(gp_plan* p, const float* V16, const int* done_flag); // one launch per term into the parent's partial slots
+inline float* partial_ptr(gp_plan* p) { return p->partial_ext ? p->partial_ext : p->partial.as<float>(); }
+inline float* vtiles_ptr(gp_plan* p) { return p->vtiles_ext ? p->vtiles_ext : p->Vtiles.as<float>(); }
+// per-slot scales of the finish kernels: nullptr = one outputscale for all slots
+inline const float* part_scale_ptr(gp_plan* p) { return p->backend == GP_BACKEND_SUM ? p->part_scale.as<float>() : nullptr; }
+inline bool plan_is_tc(const gp_plan* p) { return p->backend == GP_BACKEND_TCGEN05 || (p->backend == GP_BACKEND_SUM && p->sum_tc); }
 
 __host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -76,7 +76,7 @@ static int launch_simt_kind(gp_plan* p, const float* V16, const int* done_flag) 
   int64_t cps = p->tiles_per_split * SIMT_TJ;
 #define GP_SIMT_CASE(D)                                                                                          \
   case D:                                                                                                        \
-    kmv_simt_kernel<KIND, D><<<grid, SIMT_TI, 0, p->stream>>>(Z1, Z2, V16, p->partial.as<float>(), p->row_count, \
+    kmv_simt_kernel<KIND, D><<<grid, SIMT_TI, 0, p->stream>>>(Z1, Z2, V16, partial_ptr(p), p->row_count, \
                                                               p->n2, rows_pad, cps, p->same ? 1 : 0,             \
                                                               p->row_begin, done_flag);                          \
     break;
@@ -106,6 +106,10 @@ int kmv_simt_launch(gp_plan* p, const float* V16, const int* done_flag) {
 
 int kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
   if (p->backend == GP_BACKEND_SKI) return ski_kmv_partials(p, V16, done_flag);
+  if (p->backend == GP_BACKEND_SUM) {
+    if (p->sum_any_tc) GP_CHECK(pack_v_tiles(p, V16));
+    return sum_kmv_launch(p, V16, done_flag);
+  }
   if (p->backend == GP_BACKEND_TCGEN05) {
     GP_CHECK(pack_v_tiles(p, V16));
     return kmv_tc_launch(p, done_flag);
@@ -115,7 +119,7 @@ int kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
 
 // OUT[r, c] = os * sum_s partial[s][r][c] + noise * V16[row_begin + r][c]
 __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int nsplit, int64_t rows, int64_t rows_pad,
-                                       float os, float noise_add, const float* __restrict__ dvec, const float* __restrict__ V16,
+                                       float os, const float* __restrict__ pscale, float noise_add, const float* __restrict__ dvec, const float* __restrict__ V16,
                                        int64_t row_begin, float* __restrict__ OUT, int64_t ldo, int t, const int* __restrict__ xbad) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * TP) return;
@@ -123,8 +127,13 @@ __global__ void kmv_finish_user_kernel(const float* __restrict__ partial, int ns
   int c = (int)(idx % TP);
   if (c >= t) return;
   float s = 0.f;
-  for (int sp = 0; sp < nsplit; ++sp) s += partial[((int64_t)sp * rows_pad + r) * TP + c];
-  float o = os * s;
+  if (pscale) {   // kernel sum: slot sp belongs to the term with outputscale pscale[sp]
+    for (int sp = 0; sp < nsplit; ++sp) s = fmaf(pscale[sp], partial[((int64_t)sp * rows_pad + r) * TP + c], s);
+  } else {
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[((int64_t)sp * rows_pad + r) * TP + c];
+    s *= os;
+  }
+  float o = s;
   if (dvec) o = fmaf(dvec[row_begin + r], V16[(row_begin + r) * TP + c], o);
   else if (noise_add != 0.f) o = fmaf(noise_add, V16[(row_begin + r) * TP + c], o);
   if (*xbad) o = __int_as_float(0x7fc00000);
@@ -137,7 +146,7 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
   float na = (add_noise && p->same) ? p->noise : 0.f;
   const float* dv = (add_noise && p->same) ? p->noise_diag : nullptr;
   kmv_finish_user_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, p->stream>>>(p->partial.as<float>(), p->nparts, p->row_count,
-                                                                          rows_pad, p->outputscale, na, dv, V16, p->row_begin,
+                                                                          rows_pad, p->outputscale, part_scale_ptr(p), na, dv, V16, p->row_begin,
                                                                           OUT, ldo, t, p->xbad);
   p->launches++;
   GP_CUDA(cudaGetLastError());
@@ -328,6 +337,7 @@ using namespace gp;
 extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, int64_t ldo) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "row extraction is not available for the SKI backend");
+  GP_REQUIRE(p->backend != GP_BACKEND_SUM, GP_E_SHAPE, "row extraction of a kernel sum: call gp_krows on every term and add");
   GP_REQUIRE(m >= 0 && ldo >= p->n2, GP_E_SHAPE, "bad krows shape");
   if (m == 0) return GP_OK;
   const float* Z1 = p->same ? p->Z2.as<float>() + p->row_begin * p->DP : p->Z1.as<float>();
@@ -347,6 +357,7 @@ extern "C" int gp_krows(gp_plan* p, const int64_t* idx, int64_t m, float* OUT, i
 extern "C" int gp_kdiag(gp_plan* p, float* OUT) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "the diagonal is not available for the SKI backend");
+  GP_REQUIRE(p->backend != GP_BACKEND_SUM, GP_E_SHAPE, "diagonal of a kernel sum: call gp_kdiag on every term and add");
   if (p->same) {
     // stationary kernels: k(x,x) = outputscale (lazy_evaluated_kernel_tensor.py:107-133 evaluates kernel(diag=True))
     fill_kernel<<<(unsigned)cdiv(p->row_count, 256), 256, 0, p->stream>>>(OUT, p->row_count, p->outputscale);
@@ -372,6 +383,7 @@ extern "C" int gp_bilinear_grad(gp_plan* p, const float* Lf, int64_t ldl, const 
                                 double* grad_ls, double* grad_os) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "hyper-parameter gradients are not available for the SKI backend yet");
+  GP_REQUIRE(p->backend != GP_BACKEND_SUM, GP_E_SHAPE, "gradients of a kernel sum: call gp_bilinear_grad on every term");
   GP_REQUIRE(s >= 1, GP_E_SHAPE, "s must be >= 1");
   const bool ard = p->ls.size() > 1;
   const int nout = 1 + (ard ? p->d : 1);

@@ -370,7 +370,7 @@ static int launch_tc_kind(gp_plan* p, const int* done_flag) {
   int64_t rows_pad = p->rows_pad;
   dim3 grid((unsigned)p->ntile_i, (unsigned)p->nsplit);
   kmv_tc_kernel<KIND><<<grid, TC_THREADS, smem_bytes, p->stream>>>(
-      p->XA.as<float>(), p->XB.as<float>(), p->Vtiles.as<float>(), p->partial.as<float>(), p->KP, ns, p->ntile_j,
+      p->XA.as<float>(), p->XB.as<float>(), vtiles_ptr(p), partial_ptr(p), p->KP, ns, p->ntile_j,
       p->tiles_per_split, rows_pad, p->same ? 1 : 0, p->row_begin, done_flag, p->tc_trace);
   p->launches++;
   GP_CUDA(cudaGetLastError());
@@ -392,6 +392,9 @@ int kmv_tc_launch_kind(gp_plan* p, int kind, const int* done_flag) {
   set_error("bad kernel kind %d", kind);
   return GP_E_SHAPE;
 }
-int kmv_tc_launch(gp_plan* p, const int* done_flag) { return kmv_tc_launch_kind(p, p->kind, done_flag); }
+int kmv_tc_launch(gp_plan* p, const int* done_flag) {
+  if (p->backend == GP_BACKEND_SUM) return sum_kmv_launch(p, nullptr, done_flag);   // all terms on tensor cores (plan_is_tc)
+  return kmv_tc_launch_kind(p, p->kind, done_flag);
+}
 
 }  // namespace gp

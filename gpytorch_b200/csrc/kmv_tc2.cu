@@ -518,7 +518,7 @@ static int launch_one(gp_plan* p, const int* done_flag) {
   }
   dim3 grid((unsigned)(p->rows_pad / ROWS_CTA), (unsigned)p->nsplit);
   kmv_tc2_kernel<KIND, NPOLY, A_TMEM, TRACE><<<grid, THREADS, smem, p->stream>>>(
-      p->XA.as<float>(), p->XB.as<float>(), p->Vtiles.as<float>(), p->partial.as<float>(), p->KP, ns, p->ntile_j,
+      p->XA.as<float>(), p->XB.as<float>(), vtiles_ptr(p), partial_ptr(p), p->KP, ns, p->ntile_j,
       p->tiles_per_split, p->rows_pad, p->same ? 1 : 0, p->row_begin, done_flag, p->tc_trace);
   p->launches++;
   GP_CUDA(cudaGetLastError());

@@ -154,8 +154,8 @@ pc_step_kernel(const float* __restrict__ Z, int DP, float os, float* __restrict_
 // ---- persistent variant: ALL steps in one cooperative launch -----------------------------------------------------------
 // The step-wise path above pays a kernel launch + a last-CTA hand-off (~20 us) per step for ~2 us of work.  Here the
 // grid stays resident (cudaLaunchCooperativeKernel guarantees co-residency), every thread owns the same rows in every
-// step, and the steps are separated by two grid barriers: (A) partials written -> CTA 0 reduces them, applies the stop
-// rule and the permutation swap; (B) state published -> next step.  Arithmetic per entry is identical to pc_step_kernel.
+// step, and the steps are separated by one grid barrier (pc_persistent1_kernel below).  Arithmetic per entry is identical to
+// pc_step_kernel.
 __device__ __forceinline__ void pc_grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -170,149 +170,31 @@ __device__ __forceinline__ void pc_grid_barrier(unsigned int* bar, unsigned int 
 constexpr int PCP_THREADS = 384;  // persistent kernel: one CTA per SM keeps the grid barrier small (148 arrivals)
 constexpr int PCP_RED = 512;
 
-template <int KIND>
-__global__ void __launch_bounds__(PCP_THREADS)
-pc_persistent_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, int64_t n, int max_rank, float tol,
-                     float* diag, int* perm, int* pos, PcState* st, int64_t* piv_out, float* pval, int* ppos, double* psum) {
-  extern __shared__ float sh[];
-  float* zp = sh;           // [DP]
-  float* lp = sh + DP;      // [max_rank]   L[q][pivot]
-  float* col = lp + max_rank;  // [max_rank][PCP_THREADS]: L[q][j] of this thread's FIRST row (the dot product below is
-                               // latency bound on L2 when it re-reads the column from Lt: 1.4 ms -> per 100 steps)
-  __shared__ float s_val[PCP_RED];   // reduction trees run over PCP_RED = 512 slots; slots >= PCP_THREADS stay neutral
-  __shared__ int s_pos[PCP_RED];
-  __shared__ double s_sum[PCP_RED];
-  const int tid = threadIdx.x;
-  if (tid < PCP_RED - PCP_THREADS) { s_val[PCP_THREADS + tid] = -INFINITY; s_pos[PCP_THREADS + tid] = 0x7fffffff; s_sum[PCP_THREADS + tid] = 0.0; }
-  const int64_t stride = (int64_t)gridDim.x * PCP_THREADS;
-  const int64_t jfirst = (int64_t)blockIdx.x * PCP_THREADS + tid;
-  unsigned int nbar = 0;
-  for (int m = 0; m < max_rank; ++m) {
-    const int pi = *((volatile int*)&st->pivot);
-    const float dpiv = *((volatile float*)&st->dpiv);
-    for (int c = tid; c < DP; c += PCP_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
-    for (int q = tid; q < m; q += PCP_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM
-    __syncthreads();
-    float best = -INFINITY;
-    int best_pos = 0x7fffffff;
-    double asum = 0.0;
-    float* Lm = Lt + (int64_t)m * n;
-    for (int64_t j = (int64_t)blockIdx.x * PCP_THREADS + tid; j < n; j += stride) {
-      const int pj = __ldcg(pos + j);
-      const bool cached = (j == jfirst);
-      if (pj < m) {
-        Lm[j] = 0.f;
-        if (cached) col[m * PCP_THREADS + tid] = 0.f;
-      } else if (pj == m) {
-        Lm[j] = dpiv;
-        if (cached) col[m * PCP_THREADS + tid] = dpiv;
-      } else {
-        float s = 0.f;
-        for (int c = 0; c < DP; ++c) {
-          float df = zp[c] - Z[j * DP + c];
-          s = fmaf(df, df, s);
-        }
-        float v = os * cov_from_arg<KIND>(-0.5f * s);
-        {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int q = 0;
-          if (cached) {   // same values, same order as the global-memory branch: bit-identical
-            const float* cj = col + tid;
-            for (; q + 4 <= m; q += 4) {
-              s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
-              s1 = fmaf(lp[q + 1], cj[(q + 1) * PCP_THREADS], s1);
-              s2 = fmaf(lp[q + 2], cj[(q + 2) * PCP_THREADS], s2);
-              s3 = fmaf(lp[q + 3], cj[(q + 3) * PCP_THREADS], s3);
-            }
-            for (; q < m; ++q) s0 = fmaf(lp[q], cj[q * PCP_THREADS], s0);
-          } else {
-            for (; q + 4 <= m; q += 4) {
-              s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);          // column j is only ever written by this thread
-              s1 = fmaf(lp[q + 1], Lt[(int64_t)(q + 1) * n + j], s1);
-              s2 = fmaf(lp[q + 2], Lt[(int64_t)(q + 2) * n + j], s2);
-              s3 = fmaf(lp[q + 3], Lt[(int64_t)(q + 3) * n + j], s3);
-            }
-            for (; q < m; ++q) s0 = fmaf(lp[q], Lt[(int64_t)q * n + j], s0);
-          }
-          v -= (s0 + s1) + (s2 + s3);
-        }
-        v /= dpiv;
-        Lm[j] = v;
-        if (cached) col[m * PCP_THREADS + tid] = v;
-        const float dn = diag[j] - v * v;
-        diag[j] = dn;
-        float cv; int cp;
-        if (dn != dn) { cv = INFINITY; cp = -1; }  // NaN poisons the selection
-        else { cv = dn; cp = pj; }
-        if (cv > best || (cv == best && cp < best_pos)) { best = cv; best_pos = cp; }
-        asum += fabs((double)dn);
-      }
-    }
-    s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
-    __syncthreads();
-    for (int s = PCP_RED / 2; s > 0; s >>= 1) {
-      if (tid < s && tid + s < PCP_RED) {
-        float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
-        if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
-        s_sum[tid] += s_sum[tid + s];
-      }
-      __syncthreads();
-    }
-    if (tid == 0) { pval[blockIdx.x] = s_val[0]; ppos[blockIdx.x] = s_pos[0]; psum[blockIdx.x] = s_sum[0]; }
-    pc_grid_barrier(&st->bar, (++nbar) * gridDim.x);   // (A) all partials are visible
-    if (blockIdx.x == 0) {
-      best = -INFINITY; best_pos = 0x7fffffff; asum = 0.0;
-      for (int b = tid; b < (int)gridDim.x; b += PCP_THREADS) {   // fixed assignment + fixed tree => deterministic
-        float v2 = __ldcg(pval + b); int p2 = __ldcg(ppos + b);
-        if (v2 > best || (v2 == best && p2 < best_pos)) { best = v2; best_pos = p2; }
-        asum += __ldcg(psum + b);
-      }
-      s_val[tid] = best; s_pos[tid] = best_pos; s_sum[tid] = asum;
-      __syncthreads();
-      for (int s = PCP_RED / 2; s > 0; s >>= 1) {
-        if (tid < s) {
-          float v2 = s_val[tid + s]; int p2 = s_pos[tid + s];
-          if (v2 > s_val[tid] || (v2 == s_val[tid] && p2 < s_pos[tid])) { s_val[tid] = v2; s_pos[tid] = p2; }
-          s_sum[tid] += s_sum[tid + s];
-        }
-        __syncthreads();
-      }
-      if (tid == 0) {
-        const double tot = s_sum[0];
-        st->rank = m + 1;
-        const float err = (float)(tot / (double)st->orig_err);
-        st->err = err;
-        const float mx = s_val[0];
-        const int pp = s_pos[0];
-        if (m + 1 >= max_rank || (int64_t)(m + 1) >= n || !(err > tol)) {
-          st->done = 1;
-        } else if (pp < 0 || !(mx > 0.f)) {
-          st->nan_flag = 1;
-          st->done = 1;
-        } else {
-          const int pi_new = perm[pp];
-          const int pi_old = perm[m + 1];
-          perm[m + 1] = pi_new; perm[pp] = pi_old;
-          pos[pi_new] = m + 1; pos[pi_old] = pp;
-          st->pivot = pi_new;
-          st->dpiv = sqrtf(mx);
-          piv_out[m + 1] = (int64_t)pi_new;
-        }
-      }
-    }
-    pc_grid_barrier(&st->bar, (++nbar) * gridDim.x);   // (B) state + swap are visible
-    if (*((volatile int*)&st->done)) break;
-  }
-}
-
-// Single-barrier form of the persistent kernel.  Every CTA reduces the per-CTA partials itself (same loads, same tree => the
-// same pivot, error and stop decision everywhere), so the second grid barrier of pc_persistent_kernel ("state published") is
-// not needed: nothing global is read back except the partials, which are double-buffered by step parity (a CTA can only
+// Persistent kernel with ONE grid barrier per step.  Every CTA reduces the per-CTA partials itself (same loads, same tree => the
+// same pivot, error and stop decision everywhere), so no second barrier ("state published"; the round-1 form had one) is
+// needed: nothing global is read back except the partials, which are double-buffered by step parity (a CTA can only
 // overwrite buffer m & 1 at step m + 2, i.e. after barrier m + 1, which every CTA reaches after it has read the step-m
 // partials).  The permutation is not materialised: a row's position is private to the thread that owns the row (pos[j],
 // patched by the owner when the row is swapped), the winning partial carries its row index, and the row that sits at
 // position m + 1 (the one the swap moves to the winner's old position) announces itself through one more partial.
-// Arithmetic, tie-breaking (earliest position) and reduction order are those of pc_persistent_kernel: bit-identical pivots.
+// Arithmetic and tie-breaking (earliest position) per entry are those of pc_step_kernel: bit-identical pivots.
+// kernel sums (GP_BACKEND_SUM): K[pivot, j] = sum_t os_t k_t(|z_t,pivot - z_t,j|^2), every term with its own packed inputs
+constexpr int PC_KIND_SUM = 64;
+struct PcTerms {
+  int n;
+  int kind[4], DP[4];
+  float os[4];
+  const float* Z[4];
+};
+__device__ __forceinline__ float pc_cov_rt(int kind, float a) {
+  switch (kind) {
+    case GP_RBF: return cov_from_arg<GP_RBF>(a);
+    case GP_MATERN12: return cov_from_arg<GP_MATERN12>(a);
+    case GP_MATERN32: return cov_from_arg<GP_MATERN32>(a);
+    default: return cov_from_arg<GP_MATERN52>(a);
+  }
+}
+
 struct PcPart {
   double sum;
   float val;
@@ -322,7 +204,7 @@ struct PcPart {
 template <int KIND>
 __global__ void __launch_bounds__(PCP_THREADS)
 pc_persistent1_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, int64_t n, int max_rank, float tol,
-                      float* diag, int* pos, PcState* st, int64_t* piv_out, PcPart* part) {
+                      float* diag, int* pos, PcState* st, int64_t* piv_out, PcPart* part, const PcTerms tt) {
   extern __shared__ float sh[];
   float* zp = sh;
   float* lp = sh + DP;
@@ -347,7 +229,15 @@ pc_persistent1_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, 
   auto better = [](float v2, int p2, float v1, int p1) { return v2 > v1 || (v2 == v1 && p2 < p1); };
   for (int m = 0; m < max_rank; ++m) {
     if (tid == 0) s_old = -1;
-    for (int c = tid; c < DP; c += PCP_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+    if (KIND == PC_KIND_SUM) {   // DP = sum of the terms' widths: the pivot rows of all terms back to back
+      int off = 0;
+      for (int t = 0; t < tt.n; ++t) {
+        for (int c = tid; c < tt.DP[t]; c += PCP_THREADS) zp[off + c] = tt.Z[t][(int64_t)pi * tt.DP[t] + c];
+        off += tt.DP[t];
+      }
+    } else {
+      for (int c = tid; c < DP; c += PCP_THREADS) zp[c] = Z[(int64_t)pi * DP + c];
+    }
     for (int q = tid; q < m; q += PCP_THREADS) lp[q] = __ldcg(Lt + (int64_t)q * n + pi);   // written by another SM, before the last barrier
     __syncthreads();
     float best = -INFINITY;
@@ -367,12 +257,28 @@ pc_persistent1_kernel(const float* __restrict__ Z, int DP, float os, float* Lt, 
         Lm[j] = dpiv;
         if (cached) col[m * PCP_THREADS + tid] = dpiv;
       } else {
-        float s = 0.f;
-        for (int c = 0; c < DP; ++c) {
-          float df = zp[c] - Z[j * DP + c];
-          s = fmaf(df, df, s);
+        float v;
+        if (KIND == PC_KIND_SUM) {
+          v = 0.f;
+          int off = 0;
+          for (int t = 0; t < tt.n; ++t) {
+            const float* zj = tt.Z[t] + j * tt.DP[t];
+            float s = 0.f;
+            for (int c = 0; c < tt.DP[t]; ++c) {
+              float df = zp[off + c] - zj[c];
+              s = fmaf(df, df, s);
+            }
+            v = fmaf(tt.os[t], pc_cov_rt(tt.kind[t], -0.5f * s), v);
+            off += tt.DP[t];
+          }
+        } else {
+          float s = 0.f;
+          for (int c = 0; c < DP; ++c) {
+            float df = zp[c] - Z[j * DP + c];
+            s = fmaf(df, df, s);
+          }
+          v = os * cov_from_arg<(KIND == PC_KIND_SUM ? GP_RBF : KIND)>(-0.5f * s);
         }
-        float v = os * cov_from_arg<KIND>(-0.5f * s);
         {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           int q = 0;
@@ -674,6 +580,7 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
   GP_REQUIRE(p->same, GP_E_SHAPE, "pivoted Cholesky needs a square operator");
   GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "pivoted Cholesky is not available for the SKI backend");
+  GP_CHECK(sum_prepare(p));
   const int64_t n = p->n2;
   GP_REQUIRE(n < (int64_t)1 << 31, GP_E_SHAPE, "n too large");
   rank = (int)std::min<int64_t>(rank, n);
@@ -693,50 +600,51 @@ extern "C" int gp_pivoted_cholesky(gp_plan* p, int rank, float error_tol, float*
   int* ppos = reinterpret_cast<int*>(pval + gb);
   GP_CUDA(cudaMemsetAsync(Lt, 0, sizeof(float) * (size_t)rank * n, st));
   GP_CUDA(cudaMemsetAsync(piv, 0, sizeof(int64_t) * rank, st));
-  pc_init_kernel<<<gb, PC_THREADS, 0, st>>>(diag, perm, pos, n, p->outputscale, S, piv);
+  const bool sum = p->backend == GP_BACKEND_SUM;
+  PcTerms tt;
+  memset(&tt, 0, sizeof(tt));
+  float os_total = p->outputscale;
+  int dp_total = p->DP;
+  if (sum) {
+    os_total = 0.f;
+    dp_total = 0;
+    tt.n = (int)p->terms.size();
+    for (int t = 0; t < tt.n; ++t) {
+      const gp_plan* q = p->terms[t];
+      tt.kind[t] = q->kind; tt.DP[t] = q->DP; tt.os[t] = q->outputscale; tt.Z[t] = q->Z2.as<float>();
+      os_total += q->outputscale;
+      dp_total += q->DP;
+    }
+  }
+  pc_init_kernel<<<gb, PC_THREADS, 0, st>>>(diag, perm, pos, n, os_total, S, piv);   // stationary terms: constant initial diagonal
   p->launches += 1;
-  const float* Z = p->Z2.as<float>();
+  const float* Z = sum ? nullptr : p->Z2.as<float>();
   const bool stepwise = getenv("GP_PC_STEPWISE") != nullptr;   // debugging / A-B switch: one launch per step
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device);
+  GP_REQUIRE(!sum || (coop && !stepwise), GP_E_STATE, "pivoted Cholesky of a kernel sum needs the cooperative kernel");
   if (coop && !stepwise) {
-    const size_t sh = sizeof(float) * (p->DP + rank + (size_t)rank * PCP_THREADS);
-    const void* fn;
-    switch (p->kind) {
-      case GP_RBF: fn = (const void*)pc_persistent_kernel<GP_RBF>; break;
-      case GP_MATERN12: fn = (const void*)pc_persistent_kernel<GP_MATERN12>; break;
-      case GP_MATERN32: fn = (const void*)pc_persistent_kernel<GP_MATERN32>; break;
-      default: fn = (const void*)pc_persistent_kernel<GP_MATERN52>; break;
+    const size_t sh = sizeof(float) * (dp_total + rank + (size_t)rank * PCP_THREADS);
+    const void* fn1;
+    switch (sum ? PC_KIND_SUM : p->kind) {
+      case GP_RBF: fn1 = (const void*)pc_persistent1_kernel<GP_RBF>; break;
+      case GP_MATERN12: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN12>; break;
+      case GP_MATERN32: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN32>; break;
+      case PC_KIND_SUM: fn1 = (const void*)pc_persistent1_kernel<PC_KIND_SUM>; break;
+      default: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN52>; break;
     }
-    GP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    int per_sm = 0;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PCP_THREADS, sh));
-    GP_REQUIRE(per_sm >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
-    const unsigned grid = (unsigned)std::min<int64_t>(std::min<int64_t>(gb, cdiv(n, PCP_THREADS)), (int64_t)per_sm * p->n_sm);  // <= gb partial slots
-    int DPv = p->DP, rk = rank;
-    float osv = p->outputscale, tolv = error_tol;
+    GP_CUDA(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    int per_sm1 = 0;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn1, PCP_THREADS, sh));
+    GP_REQUIRE(per_sm1 >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
+    const unsigned grid1 = (unsigned)std::min<int64_t>(cdiv(n, PCP_THREADS), (int64_t)per_sm1 * p->n_sm);
+    GP_CHECK(p->pcpart.ensure(sizeof(PcPart) * 2 * (size_t)grid1));
+    PcPart* part = p->pcpart.as<PcPart>();
+    int DPv = dp_total, rk = rank;
+    float osv = os_total, tolv = error_tol;
     int64_t nn = n;
-    if (getenv("GP_PC_TWOBAR") != nullptr) {   // A-B switch: the two-barrier form (CTA 0 reduces, second barrier publishes)
-      void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &perm, &pos, &S, &piv, &pval, &ppos, &psum};
-      GP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PCP_THREADS), args, sh, st));
-    } else {
-      const void* fn1;
-      switch (p->kind) {
-        case GP_RBF: fn1 = (const void*)pc_persistent1_kernel<GP_RBF>; break;
-        case GP_MATERN12: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN12>; break;
-        case GP_MATERN32: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN32>; break;
-        default: fn1 = (const void*)pc_persistent1_kernel<GP_MATERN52>; break;
-      }
-      GP_CUDA(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      int per_sm1 = 0;
-      GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn1, PCP_THREADS, sh));
-      GP_REQUIRE(per_sm1 >= 1, GP_E_CUDA, "pivoted Cholesky kernel does not fit on an SM");
-      const unsigned grid1 = (unsigned)std::min<int64_t>(cdiv(n, PCP_THREADS), (int64_t)per_sm1 * p->n_sm);
-      GP_CHECK(p->pcpart.ensure(sizeof(PcPart) * 2 * (size_t)grid1));
-      PcPart* part = p->pcpart.as<PcPart>();
-      void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &pos, &S, &piv, &part};
-      GP_CUDA(cudaLaunchCooperativeKernel(fn1, dim3(grid1), dim3(PCP_THREADS), args, sh, st));
-    }
+    void* args[] = {(void*)&Z, &DPv, &osv, &Lt, &nn, &rk, &tolv, &diag, &pos, &S, &piv, &part, &tt};
+    GP_CUDA(cudaLaunchCooperativeKernel(fn1, dim3(grid1), dim3(PCP_THREADS), args, sh, st));
     p->launches += 1;
   } else {
   for (int m = 0; m < rank; ++m) {

@@ -105,6 +105,17 @@ class Plan:
             check(self.lib.gp_plan_set_ski(self._h, gs, lo, st, d))
         return self
 
+    def set_sum(self, terms):
+        """Kernel sum (AdditiveKernel): this plan's operator becomes sum_t K_t (+ its own noise).  `terms` are ready plans over
+        the same rows (their own kind / lengthscales / outputscale / active dimensions); they must outlive this plan.  Call after
+        set_hypers (only the noise of this plan is used)."""
+        terms = list(terms)
+        arr = (C.c_void_p * len(terms))(*[t._h.value for t in terms])
+        self._terms = terms                       # keep them alive
+        with torch.cuda.device(self.device):
+            check(self.lib.gp_plan_set_sum(self._h, arr, len(terms)))
+        return self
+
     def set_noise_diag(self, diag: torch.Tensor | None):
         """Per-row noise variances (FixedNoiseGaussianLikelihood): K_hat = K + diag(d).  None restores the scalar noise."""
         if diag is None:
@@ -119,7 +130,7 @@ class Plan:
     def info(self):
         b, s, k, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(self.lib.gp_plan_info(self._h, C.byref(b), C.byref(s), C.byref(k), C.byref(m)))
-        return {"backend": {1: "tcgen05", 2: "simt", 3: "ski"}.get(b.value, "?"), "nsplit": s.value, "kpad": k.value, "n_sm": m.value}
+        return {"backend": {1: "tcgen05", 2: "simt", 3: "ski", 4: "sum"}.get(b.value, "?"), "nsplit": s.value, "kpad": k.value, "n_sm": m.value}
 
     def time_kmv_kernel(self, v: torch.Tensor, warmup: int = 3, reps: int = 20) -> float:
         """Average device time (ms) of ONE launch of the fused K.V kernel alone (CUDA events on the plan stream)."""

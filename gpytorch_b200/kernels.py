@@ -1,4 +1,4 @@
-"""gpytorch.kernels.{Kernel, RBFKernel, MaternKernel, ScaleKernel} for the accelerated path.
+"""gpytorch.kernels.{Kernel, RBFKernel, MaternKernel, ScaleKernel, AdditiveKernel, GridInterpolationKernel} for the accelerated path.
 
 Same constructor kwargs and call contract as the reference (kernels/kernel.py:163-171, :454-534;
 rbf_kernel.py:68-85; matern_kernel.py:79-110; scale_kernel.py:64-118), but `forward` returns an
@@ -48,6 +48,13 @@ class Kernel(Module):
 
     def forward(self, x1, x2, diag=False, **params):
         raise NotImplementedError
+
+    def __add__(self, other):
+        # k1 + k2 -> AdditiveKernel with nested sums flattened (kernels/kernel.py:541-545)
+        parts = []
+        for k in (self, other):
+            parts.extend(k.kernels if isinstance(k, AdditiveKernel) else (k,))
+        return AdditiveKernel(*parts)
 
     def _batch_size(self):
         return self.batch_shape[0] if len(self.batch_shape) else None
@@ -148,6 +155,16 @@ class ScaleKernel(Kernel):
 
     def forward(self, x1, x2, diag=False, _same=False, _batch_index=None, **params):
         bi = _batch_index if len(self.base_kernel.batch_shape) else None
+        if isinstance(self.base_kernel, AdditiveKernel):
+            # s (k_1 + ... + k_m): the scale is distributed over the terms' folded outputscales (autograd sees the products)
+            from .operators import SumKernelLinearOperator
+            if _batch_index is not None:
+                raise NotImplementedError("batched ScaleKernel over an AdditiveKernel")
+            inner = self.base_kernel(x1, None if _same else x2)
+            terms = inner.ops if isinstance(inner, SumKernelLinearOperator) else [inner]
+            scaled = [KernelLinearOperator(t.x1, t.x2, t.kind, t.lengthscale, self.outputscale * t.outputscale) for t in terms]
+            op = scaled[0] if len(scaled) == 1 else SumKernelLinearOperator(scaled)
+            return op.diagonal() if diag else op
         if isinstance(self.base_kernel, GridInterpolationKernel):
             base = self.base_kernel.forward(x1, x2, diag=False, _same=_same, **params)
         else:
@@ -166,6 +183,36 @@ class ScaleKernel(Kernel):
             x1 = x1.index_select(-1, idx)
             x2 = None if x2 is None else x2.index_select(-1, idx)
         return Kernel.__call__(self, x1, x2, diag=diag, **params)
+
+
+class AdditiveKernel(Kernel):
+    """k = k_1 + ... + k_m (kernels/kernel.py:592-621).  Every component is called on the full inputs (so its own active_dims
+    apply, as in the reference) and must produce an engine kernel operator; the sum is ONE SumKernelLinearOperator whose
+    products / solves run natively (gp_plan_set_sum), not a dense addition."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        for k in kernels:
+            if not isinstance(k, Kernel):
+                raise RuntimeError("AdditiveKernel components must be kernels")
+            if len(k.batch_shape):
+                raise NotImplementedError("batched components of an AdditiveKernel")
+        self.kernels = torch.nn.ModuleList(kernels)
+
+    def forward(self, x1, x2, diag=False, **params):
+        raise NotImplementedError("AdditiveKernel dispatches to its components in __call__")
+
+    def __call__(self, x1, x2=None, diag=False, **params):
+        from .operators import SKIKernelLinearOperator, SumKernelLinearOperator
+        terms = [k(x1, x2, diag=diag, **params) for k in self.kernels]
+        if diag:
+            out = terms[0]
+            for t in terms[1:]:
+                out = out + t
+            return out
+        if any(isinstance(t, SKIKernelLinearOperator) or not isinstance(t, KernelLinearOperator) for t in terms):
+            raise NotImplementedError("AdditiveKernel components must be RBF / Matern kernels (optionally scaled) on the accelerated path")
+        return terms[0] if len(terms) == 1 else SumKernelLinearOperator(terms)
 
 
 class GridInterpolationKernel(Kernel):

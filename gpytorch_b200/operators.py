@@ -67,6 +67,8 @@ def _get_plan_locked(x1, x2, backend, row_begin, row_count, comm) -> Plan:
 
 def clear_plan_cache():
     with _PLAN_LOCK:
+        while _SUM_PLANS:
+            _SUM_PLANS.popitem()[1].close()
         while _PLAN_CACHE:
             _PLAN_CACHE.popitem()[1].close()
 
@@ -192,6 +194,15 @@ class KernelLinearOperator:
     def representation(self):
         return (self.x1, self.x2, self.lengthscale, self.outputscale)
 
+    def hyper_tensors(self):
+        """The differentiable hyper-parameters of this operator, in the order _bilinear_derivative_list returns their
+        gradients (the autograd functions below take them as explicit inputs)."""
+        return [self.lengthscale, self.outputscale]
+
+    def _bilinear_derivative_list(self, left, right):
+        gl, go = self._bilinear_derivative(left, right)
+        return [gl.reshape(self.lengthscale.shape), go.reshape(self.outputscale.shape)]
+
     # -- LinearOperator protocol: shape helpers / transpose (lazy_evaluated_kernel_tensor.py:277-341) --
     def _size(self):
         return self.shape
@@ -229,7 +240,7 @@ class KernelLinearOperator:
 
     # -- products --
     def matmul(self, rhs):
-        return _KernelMatmul.apply(self, rhs, self.lengthscale, self.outputscale)
+        return _KernelMatmul.apply(self, rhs, *self.hyper_tensors())
 
     __matmul__ = matmul
     _matmul = matmul
@@ -274,6 +285,102 @@ class KernelLinearOperator:
         """(d/d lengthscale, d/d outputscale) of sum(left * (K @ right)); lazy_evaluated_kernel_tensor.py:69-105."""
         gl, go = self.plan(getattr(self, "_last_noise", 0.0)).bilinear_grad(left, right)
         return torch.tensor(gl, device=self.device, dtype=self.dtype), torch.tensor(go, device=self.device, dtype=self.dtype)
+
+
+class SumKernelLinearOperator(KernelLinearOperator):
+    """K_1 + ... + K_m over the same inputs (AdditiveKernel, kernels/kernel.py:592-621).  The reference evaluates every term
+    densely and adds the matrices; here the sum is ONE engine operator (gp_plan_set_sum): a product launches the fused kernel of
+    every term into disjoint partial slots, the solves / preconditioner / SLQ run on the sum, and the hyper-parameter gradients
+    of each term come from that term's own bilinear derivative with the shared left / right factors."""
+
+    def __init__(self, ops):
+        ops = list(ops)
+        flat = []
+        for o in ops:
+            flat.extend(o.ops if isinstance(o, SumKernelLinearOperator) else [o])
+        if not 1 <= len(flat) <= 4:
+            raise RuntimeError(f"a kernel sum takes 1 to 4 terms (got {len(flat)})")
+        first = flat[0]
+        for o in flat[1:]:
+            if o.shape != first.shape or o.same != first.same:
+                raise RuntimeError(f"cannot add kernels of shapes {tuple(first.shape)} and {tuple(o.shape)}")
+        self.ops = flat
+        self.x1, self.x2, self.same = first.x1, first.x2, first.same
+        self.kind = "sum"
+        self.lengthscale, self.outputscale = first.lengthscale, first.outputscale   # representative only (device / dtype)
+        self._comm, self._row_begin, self._row_count = first._comm, first._row_begin, first._row_count
+        self._plan = None
+
+    def hyper_tensors(self):
+        return [t for o in self.ops for t in o.hyper_tensors()]
+
+    def _bilinear_derivative_list(self, left, right):
+        out = []
+        for o in self.ops:
+            o._last_noise = 0.0
+            out.extend(o._bilinear_derivative_list(left, right))
+        return out
+
+    @property
+    def requires_grad(self):
+        return any(o.requires_grad for o in self.ops)
+
+    def representation(self):
+        return tuple(t for o in self.ops for t in o.representation())
+
+    def plan(self, noise=0.0) -> Plan:
+        terms = [o.plan(0.0) for o in self.ops]
+        nz = float(noise.detach().reshape(-1)[0]) if torch.is_tensor(noise) else float(noise)
+        with _PLAN_LOCK:
+            key = ("sum", tuple(id(t) for t in terms))
+            parent = _SUM_PLANS.pop(key, None)
+            if parent is None:
+                parent = Plan(self.x1, None if self.same else self.x2, backend="auto", row_begin=self._row_begin,
+                              row_count=self._row_count, comm=self._comm)
+                parent._hyp_key = None
+            _SUM_PLANS[key] = parent
+            while len(_SUM_PLANS) > 16:
+                _SUM_PLANS.pop(next(iter(_SUM_PLANS))).close()
+        # the terms may have been re-created / re-packed since the last use: (re-)attach them every time (validation + a
+        # 64-float upload, no allocation), then set the noise of the sum
+        parent.set_sum(terms)
+        if parent._hyp_key != nz:
+            parent.set_hypers("rbf", [1.0], 1.0, nz)
+            parent._hyp_key = nz
+        self._plan = parent
+        return parent
+
+    def _transpose_nonbatch(self):
+        return self if self.same else SumKernelLinearOperator([o._transpose_nonbatch() for o in self.ops])
+
+    def detach(self):
+        return SumKernelLinearOperator([o.detach() for o in self.ops])
+
+    def to_dense(self):
+        out = self.ops[0].to_dense()
+        for o in self.ops[1:]:
+            out = out + o.to_dense()
+        return out
+
+    def diagonal(self, dim1=-2, dim2=-1):
+        out = self.ops[0].diagonal()
+        for o in self.ops[1:]:
+            out = out + o.diagonal()
+        return out
+
+    _diagonal = diagonal
+
+    def __getitem__(self, index):
+        parts = [o[index] for o in self.ops]
+        if torch.is_tensor(parts[0]):
+            return sum(parts[1:], parts[0])
+        return SumKernelLinearOperator(parts)
+
+    def _bilinear_derivative(self, left, right):
+        raise NotImplementedError("a kernel sum has one (lengthscale, outputscale) pair per term: use _bilinear_derivative_list")
+
+
+_SUM_PLANS: "dict[tuple, Plan]" = {}
 
 
 class SKIKernelLinearOperator(KernelLinearOperator):
@@ -321,7 +428,7 @@ class SKIKernelLinearOperator(KernelLinearOperator):
 
 class _KernelMatmul(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, op, rhs, lengthscale, outputscale):
+    def forward(ctx, op, rhs, *hypers):
         ctx.op = op
         out = op.plan(getattr(op, "_last_noise", 0.0)).kmv(rhs.detach())
         ctx.save_for_backward(rhs.detach())
@@ -335,19 +442,19 @@ class _KernelMatmul(torch.autograd.Function):
         vec = g.dim() == 1
         g2 = g.unsqueeze(-1) if vec else g
         r2 = rhs.unsqueeze(-1) if vec else rhs
-        grad_rhs = grad_ls = grad_os = None
+        grad_rhs = None
+        nh = len(ctx.needs_input_grad) - 2
+        grads = [None] * nh
         if ctx.needs_input_grad[1]:
             # K^T g: for x1 == x2 the operator is symmetric
             if not op.same:
-                opT = KernelLinearOperator(op.x2, op.x1, op.kind, op.lengthscale, op.outputscale)
-                grad_rhs = opT.plan().kmv(g)
+                grad_rhs = op._transpose_nonbatch().plan().kmv(g)
             else:
                 grad_rhs = op.plan(getattr(op, "_last_noise", 0.0)).kmv(g)
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            gl, go = op._bilinear_derivative(g2, r2)
-            grad_ls = gl.reshape(op.lengthscale.shape) if ctx.needs_input_grad[2] else None
-            grad_os = go.reshape(op.outputscale.shape) if ctx.needs_input_grad[3] else None
-        return None, grad_rhs, grad_ls, grad_os
+        if any(ctx.needs_input_grad[2:]):
+            gs = op._bilinear_derivative_list(g2, r2)
+            grads = [gi if need else None for gi, need in zip(gs, ctx.needs_input_grad[2:])]
+        return (None, grad_rhs, *grads)
 
 
 class AddedDiagLinearOperator:
@@ -514,7 +621,7 @@ class AddedDiagLinearOperator:
 
     def solve(self, rhs, lhs=None):
         """K_hat^{-1} rhs by preconditioned CG (LinearOperator.solve -> linear_cg, n_tridiag = 0)."""
-        out = _Solve.apply(self, rhs, self.kernel_op.lengthscale, self.kernel_op.outputscale, self._noise_param)
+        out = _Solve.apply(self, rhs, self._noise_param, *self.kernel_op.hyper_tensors())
         return out if lhs is None else lhs @ out
 
     def inv_quad_logdet(self, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True):
@@ -526,8 +633,7 @@ class AddedDiagLinearOperator:
         rhs = inv_quad_rhs
         if rhs is not None and rhs.dim() == 1:
             rhs = rhs.unsqueeze(-1)
-        iq, ld = _InvQuadLogdet.apply(self, rhs, bool(logdet), self.kernel_op.lengthscale, self.kernel_op.outputscale,
-                                      self._noise_param)
+        iq, ld = _InvQuadLogdet.apply(self, rhs, bool(logdet), self._noise_param, *self.kernel_op.hyper_tensors())
         if rhs is None:
             iq = torch.empty(0, device=self.device)
         elif reduce_inv_quad:
@@ -684,7 +790,7 @@ def _run_cg(op: AddedDiagLinearOperator, rhs, n_tridiag, w):
 
 class _Solve(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, op, rhs, lengthscale, outputscale, noise):
+    def forward(ctx, op, rhs, noise, *hypers):
         vec = rhs.dim() == 1
         r2 = (rhs.unsqueeze(-1) if vec else rhs).detach().float().contiguous()
         n = op.shape[0]
@@ -710,22 +816,22 @@ class _Solve(torch.autograd.Function):
             w, _, _ = op._preconditioner()
             gsol, _, _ = _run_cg(op, g, 0, w)
         grad_rhs = (gsol.squeeze(-1) if ctx.vec else gsol) if ctx.needs_input_grad[1] else None
-        gl = go = gn = None
+        gn = None
+        grads = [None] * (len(ctx.needs_input_grad) - 3)
         if any(ctx.needs_input_grad[2:]):
-            dls, dos = op.kernel_op._bilinear_derivative(-gsol, sol)
-            gl = dls.reshape(op.kernel_op.lengthscale.shape) if ctx.needs_input_grad[2] else None
-            go = dos.reshape(op.kernel_op.outputscale.shape) if ctx.needs_input_grad[3] else None
-            gn = None
-            if ctx.needs_input_grad[4]:
+            if any(ctx.needs_input_grad[3:]):
+                gs = op.kernel_op._bilinear_derivative_list(-gsol, sol)
+                grads = [gi if need else None for gi, need in zip(gs, ctx.needs_input_grad[3:])]
+            if ctx.needs_input_grad[2]:
                 gn = (-(gsol * sol).sum(-1)) if op.per_row else (-(gsol * sol).sum()).reshape(op.diag.diag_value.shape)
-        return None, grad_rhs, gl, go, gn
+        return (None, grad_rhs, gn, *grads)
 
 
 class _InvQuadLogdet(torch.autograd.Function):
     """linear_operator.functions._inv_quad_logdet.InvQuadLogdet."""
 
     @staticmethod
-    def forward(ctx, op, rhs, want_logdet, lengthscale, outputscale, noise):
+    def forward(ctx, op, rhs, want_logdet, noise, *hypers):
         n = op.shape[0]
         dev = op.device
         ctx.op, ctx.want_logdet, ctx.has_rhs = op, want_logdet, rhs is not None
@@ -768,8 +874,9 @@ class _InvQuadLogdet(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_iq, grad_ld):
         op = ctx.op
-        gl = go = gn = grad_rhs = None
-        need_k = ctx.needs_input_grad[3] or ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        gn = grad_rhs = None
+        grads = [None] * (len(ctx.needs_input_grad) - 4)
+        need_k = any(ctx.needs_input_grad[3:])
         if ctx.mode == "chol":
             chol, sol = ctx.saved_tensors
             n = op.shape[0]
@@ -808,11 +915,9 @@ class _InvQuadLogdet(torch.autograd.Function):
             if need_k and left_cols:
                 left = torch.cat(left_cols, -1).contiguous(); right = torch.cat(right_cols, -1).contiguous()
         if need_k and left_cols:
-            dls, dos = op.kernel_op._bilinear_derivative(left, right)
+            if any(ctx.needs_input_grad[4:]):
+                gs = op.kernel_op._bilinear_derivative_list(left, right)
+                grads = [gi if need else None for gi, need in zip(gs, ctx.needs_input_grad[4:])]
             if ctx.needs_input_grad[3]:
-                gl = dls.reshape(op.kernel_op.lengthscale.shape)
-            if ctx.needs_input_grad[4]:
-                go = dos.reshape(op.kernel_op.outputscale.shape)
-            if ctx.needs_input_grad[5]:
                 gn = (left * right).sum(-1) if op.per_row else (left * right).sum().reshape(op.diag.diag_value.shape)
-        return None, grad_rhs, None, gl, go, gn
+        return (None, grad_rhs, None, gn, *grads)

@@ -45,7 +45,8 @@ enum { GP_RBF = 0, GP_MATERN12 = 1, GP_MATERN32 = 2, GP_MATERN52 = 3 };
 
 /* which fused K.V kernel runs: GP_BACKEND_TCGEN05 = tcgen05/TMEM/bulk-TMA 3xTF32 kernel,
  * GP_BACKEND_SIMT = fp32 CUDA-core kernel (bring-up / cross-check / d > 41). */
-enum { GP_BACKEND_AUTO = 0, GP_BACKEND_TCGEN05 = 1, GP_BACKEND_SIMT = 2, GP_BACKEND_SKI = 3 /* set by gp_plan_set_ski */ };
+enum { GP_BACKEND_AUTO = 0, GP_BACKEND_TCGEN05 = 1, GP_BACKEND_SIMT = 2, GP_BACKEND_SKI = 3 /* set by gp_plan_set_ski */,
+       GP_BACKEND_SUM = 4 /* set by gp_plan_set_sum */ };
 
 typedef struct gp_plan gp_plan;   /* opaque: repacked X, workspaces, stream, comm */
 typedef struct gp_comm gp_comm;   /* opaque: NCCL communicator for row-sharded runs */
@@ -87,6 +88,16 @@ int gp_plan_set_noise_diag(gp_plan* plan, const float* diag, int64_t n);
  * Call after gp_plan_set_data (square operator); products, mBCG, SLQ, gp_mll (without preconditioner) and gp_lanczos then run
  * on the interpolated operator.  Out-of-bounds inputs fail like the reference ("Received data that was out of bounds ..."). */
 int gp_plan_set_ski(gp_plan* plan, const int* grid_sizes, const float* grid_lo, const float* grid_step, int d);
+
+/* Kernel sums (AdditiveKernel, kernels/kernel.py:592-621: k = k_1 + ... + k_m, each term with its own covariance function,
+ * lengthscale(s), outputscale and active dimensions): `plan` becomes the operator  sum_t K_t  (+ its own noise), where every
+ * K_t is a ready plan over the same rows (same n1 / n2 / row shard / stream; the data pointers may differ: active_dims).
+ * Call after gp_plan_set_data on `plan`; gp_plan_set_hypers on `plan` (before or after) supplies the sum's noise, its kind /
+ * lengthscale / outputscale are ignored.  The terms stay owned by the caller and must outlive `plan`; re-packing a term (gp_plan_set_hypers on it) is
+ * picked up by the next call on `plan`.  One K.V of the sum = one fused kernel launch per term into disjoint partial slots,
+ * reduced by the same finish kernels; gp_pivoted_cholesky evaluates rows of the sum.  n_terms in [1, 4].
+ * Hyper-parameter gradients: gp_bilinear_grad on each term plan. */
+int gp_plan_set_sum(gp_plan* plan, gp_plan* const* terms, int n_terms);
 
 /* ---- kernel seam (LazyEvaluatedKernelTensor, lazy/lazy_evaluated_kernel_tensor.py) --- */
 
