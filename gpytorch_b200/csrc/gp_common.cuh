@@ -101,7 +101,9 @@ struct gp_ski_state {
   int G[4] = {0, 0, 0, 0};
   float lo[4] = {0, 0, 0, 0}, step[4] = {0, 0, 0, 0};
   int64_t M = 0;
-  gp::DevBuf first, wts, gridA, gridB, T, flag;
+  int tile_edge[4] = {0, 0, 0, 0}, tile_num[4] = {0, 0, 0, 0}, ntiles = 0;   // spatial buckets of the points (ski.cu)
+  gp::DevBuf first, wts, gridA, gridB, gridC, gridD, T, dT, flag;
+  gp::DevBuf perm, tile_off, tile_cnt, first_s, wts_s;                        // points sorted by tile + the permutation back
 };
 
 struct gp_comm {
@@ -173,6 +175,7 @@ int kmv_finish_user(gp_plan* p, const float* V16, float* OUT, int64_t ldo, int t
 int choose_geometry(gp_plan* p);
 int ski_pack(gp_plan* p);                                               // ski.cu
 int ski_kmv_partials(gp_plan* p, const float* V16, const int* done_flag);
+int ski_bilinear(gp_plan* p, const float* L16, const float* R16, double* total);   // total[0] += <A, K_uu B>, total[1 + i] += <A, (l_i dK_uu/dl_i) B>
 int sum_pack(gp_plan* p);                                               // sum.cu: geometry / buffers of a kernel-sum plan
 int sum_prepare(gp_plan* p);                                            // refresh the per-slot outputscales (no-op for other plans)
 int sum_kmv_launch(gp_plan* p, const float* V16, const int* done_flag); // one launch per term into the parent's partial slots

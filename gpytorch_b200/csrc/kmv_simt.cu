@@ -382,10 +382,30 @@ extern "C" int gp_kdiag(gp_plan* p, float* OUT) {
 extern "C" int gp_bilinear_grad(gp_plan* p, const float* Lf, int64_t ldl, const float* Rt, int64_t ldr, int s,
                                 double* grad_ls, double* grad_os) {
   GP_REQUIRE(p && p->data_set && p->hypers_set, GP_E_STATE, "plan not ready");
-  GP_REQUIRE(p->backend != GP_BACKEND_SKI, GP_E_SHAPE, "hyper-parameter gradients are not available for the SKI backend yet");
   GP_REQUIRE(p->backend != GP_BACKEND_SUM, GP_E_SHAPE, "gradients of a kernel sum: call gp_bilinear_grad on every term");
   GP_REQUIRE(s >= 1, GP_E_SHAPE, "s must be >= 1");
   const bool ard = p->ls.size() > 1;
+  if (p->backend == GP_BACKEND_SKI) {
+    // interpolated operator: everything happens on the grid (ski.cu); one sweep per 16 columns
+    std::vector<double> tot(1 + p->d, 0.0);
+    GP_CHECK(p->misc2.ensure(sizeof(float) * p->row_count * TP));
+    GP_CHECK(p->misc3.ensure(sizeof(float) * p->n2 * TP));
+    for (int c0 = 0; c0 < s; c0 += TP) {
+      const int tc = std::min(TP, s - c0);
+      GP_CHECK(to_v16(p, Lf + c0, ldl, tc, p->row_count, p->misc2.as<float>()));
+      GP_CHECK(to_v16(p, Rt + c0, ldr, tc, p->n2, p->misc3.as<float>()));
+      GP_CHECK(ski_bilinear(p, p->misc2.as<float>(), p->misc3.as<float>(), tot.data()));
+    }
+    *grad_os = tot[0];
+    if (ard) {
+      for (int c = 0; c < p->d; ++c) grad_ls[c] = p->outputscale * tot[1 + c] / (double)p->ls[c];
+    } else {
+      double sum = 0.0;
+      for (int c = 0; c < p->d; ++c) sum += tot[1 + c];
+      grad_ls[0] = p->outputscale * sum / (double)p->ls[0];
+    }
+    return GP_OK;
+  }
   const int nout = 1 + (ard ? p->d : 1);
   std::vector<double> total(nout, 0.0);
   int64_t ntj = cdiv(p->n2, SIMT_TJ);

@@ -9,12 +9,15 @@
 //   InterpolatedLinearOperator._matmul, KroneckerProductLinearOperator / ToeplitzLinearOperator._matmul   (linear_operator, absent)
 // The interpolation matrix W (4^d non-zeros per row) is never stored expanded: per row and dimension the plan keeps the first
 // node index and the 4 one-dimensional weights (16 d + 4 d bytes per row instead of 4^d (8 + 4)); the 4^d products are re-formed
-// in registers by the scatter and gather kernels.  A product is three passes:
-//   scatter  U  = W^T V           red.global.add.v4.f32 into the [M][16] grid block (M = prod G_i; L2-resident at 100^3: 64 MB)
+// in registers by the scatter and gather kernels.  The points are bucketed once per data update by the tile of their first
+// node, so that a CTA works on the (E + 3)^d grid nodes of one tile in shared memory.  A product is three passes:
+//   scatter  U  = W^T V           per tile: shared-memory accumulation, then one red.global.add.v4.f32 per touched node into the
+//                                 [M][16] grid block (M = prod G_i; 64 MB at 100^3)
 //   modes    U' = (T_0 x ... x T_{d-1}) U   one dense [G x G] product per dimension (the Toeplitz structure saves nothing at
 //                                 G = 100: an FFT of length 2G-2 costs as many flops as the direct product)
-//   gather   out = W U'           64 float4 reads per (row, column group), written as the K.V partial block the mBCG finish
-//                                 kernels read (outputscale and noise are applied there)
+//   gather   out = W U'           per tile: node block staged in shared memory, 4^d reads per (row, column group) from there,
+//                                 written as the K.V partial block the mBCG finish kernels read (outputscale / noise applied there)
+// and the bilinear derivative (hyper-parameter gradients) is d + 1 sweeps of the mode products between two scatters and a dot.
 // HBM/L2-bound: algorithmic bytes per product = N 4^d (4 + 8) B as the reference stores W explicitly.
 #include <math.h>
 
@@ -82,65 +85,210 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// decode non-zero p (0 .. 4^d - 1; dimension 0 the most significant base-4 digit) of row r: flat grid index and weight
+// ---- spatial tiling of the points -------------------------------------------------------------------------------------------------
+// W has 4^d non-zeros per row and neighbouring points share most of their grid nodes.  Touching the [M][16] grid block once per
+// (point, node) costs 4 GB of L2 atomics / reads per product at BASELINE C5 (1.3 + 0.8 ms of a 2.3 ms product).  Instead the points
+// are bucketed ONCE per data update by the tile of their first node (edge E cells per dimension); a CTA then owns a tile, keeps
+// the (E + 3)^d nodes the tile's points can touch in shared memory (<= 85 KB), accumulates / reads them there, and exchanges
+// each node with the global grid block once per tile: ~25x less L2 traffic.
+struct SkiTiles {
+  int E[SKI_MAXD];    // tile edge in cells
+  int nt[SKI_MAXD];   // tiles per dimension
+  int ntiles;
+};
+
 template <int D>
-__device__ __forceinline__ void ski_nnz(const int* __restrict__ fr, const float* __restrict__ wr, const SkiGeom& g, int p, int64_t& idx, float& w) {
-  idx = 0;
+__device__ __forceinline__ int ski_tile_of(const int* __restrict__ fr, const SkiTiles& tl) {
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) t = t * tl.nt[i] + fr[i] / tl.E[i];
+  return t;
+}
+
+template <int D>
+__global__ void ski_tile_count_kernel(const int* __restrict__ first, int64_t n, SkiTiles tl, int* __restrict__ cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) atomicAdd(cnt + ski_tile_of<D>(first + r * D, tl), 1);
+}
+
+// exclusive scan of cnt[0..m) into off[0..m] (one CTA; m <= 2^20, once per data update); cnt is reset to 0 for the fill pass
+__global__ void __launch_bounds__(1024) ski_tile_scan_kernel(int* __restrict__ cnt, int m, int* __restrict__ off) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < m) ? cnt[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int add = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < m) { off[i] = carry + sh[threadIdx.x] - v; cnt[i] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[m] = carry;
+}
+
+// bucket fill: sorted copies of the per-point interpolation data + the permutation back to the caller's row order
+template <int D>
+__global__ void ski_tile_fill_kernel(const int* __restrict__ first, const float* __restrict__ wts, int64_t n, SkiTiles tl,
+                                     const int* __restrict__ off, int* __restrict__ cursor, int* __restrict__ perm,
+                                     int* __restrict__ first_s, float* __restrict__ wts_s) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int t = ski_tile_of<D>(first + r * D, tl);
+  const int64_t pos = off[t] + atomicAdd(cursor + t, 1);
+  perm[pos] = (int)r;
+#pragma unroll
+  for (int i = 0; i < D; ++i) first_s[pos * D + i] = first[r * D + i];
+#pragma unroll
+  for (int i = 0; i < D * 4; ++i) wts_s[pos * D * 4 + i] = wts[r * D * 4 + i];
+}
+
+// geometry of one tile's node block: base node, extent and row-major pitch per dimension (last dimension fastest)
+template <int D>
+struct SkiBlock {
+  int base[D], ext[D], pitch[D];
+  int nodes;
+};
+template <int D>
+__device__ __forceinline__ SkiBlock<D> ski_block_of(int tile, const SkiGeom& g, const SkiTiles& tl) {
+  SkiBlock<D> b;
+  int rem = tile;
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    const int tc = rem % tl.nt[i];
+    rem /= tl.nt[i];
+    b.base[i] = tc * tl.E[i];
+    b.ext[i] = min(tl.E[i] + 3, g.G[i] - b.base[i]);
+  }
+  int pch = 1;
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) { b.pitch[i] = pch; pch *= b.ext[i]; }
+  b.nodes = pch;
+  return b;
+}
+// block-local node -> flat index into the global grid block
+template <int D>
+__device__ __forceinline__ int64_t ski_block_global(const SkiBlock<D>& b, const SkiGeom& g, int node) {
+  int64_t idx = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const int c = node / b.pitch[i];
+    node -= c * b.pitch[i];
+    idx += (int64_t)(b.base[i] + c) * g.stride[i];
+  }
+  return idx;
+}
+// neighbour p (base-4 digits, dimension 0 most significant) of a point: block-local node and weight
+template <int D>
+__device__ __forceinline__ void ski_local_nnz(const int* __restrict__ fr, const float* __restrict__ wr, const SkiBlock<D>& b, int p, int& node, float& w) {
+  node = 0;
   w = 1.f;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     const int c = (p >> (2 * (D - 1 - i))) & 3;
-    idx += (int64_t)(fr[i] + c) * g.stride[i];
+    node += (fr[i] - b.base[i] + c) * b.pitch[i];
     w *= wr[i * 4 + c];
   }
 }
 
-// U[idx][c] += w V[r][c]: thread = (row, non-zero); 4^D threads per row
+// U += W^T V: one CTA per (tile, part), node block in shared memory; a warp takes a point, its lanes = 8 neighbours x 4 column groups
 template <int D>
-__global__ void ski_scatter_kernel(const int* __restrict__ first, const float* __restrict__ wts, SkiGeom g, const float* __restrict__ V16,
-                                   int64_t n, int tq /*float4 groups with data: ceil(t / 4)*/, float* __restrict__ U) {
+__global__ void __launch_bounds__(256)
+ski_scatter_tiled_kernel(const int* __restrict__ first_s, const float* __restrict__ wts_s, const int* __restrict__ perm,
+                         const int* __restrict__ off, SkiGeom g, SkiTiles tl, int parts, const float* __restrict__ V16,
+                         float* __restrict__ U) {
   constexpr int NNZ = 1 << (2 * D);
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t r = e / NNZ;
-  if (r >= n) return;
-  const int pnz = (int)(e % NNZ);
-  int64_t idx;
-  float w;
-  ski_nnz<D>(first + r * D, wts + r * D * 4, g, pnz, idx, w);
-  if (w == 0.f) return;
-  const float4* v = reinterpret_cast<const float4*>(V16 + r * TP);
-  float* u = U + idx * TP;
-  for (int q = 0; q < tq; ++q) {
-    const float4 x = v[q];
-    red_add_v4(u + 4 * q, make_float4(w * x.x, w * x.y, w * x.z, w * x.w));
+  extern __shared__ __align__(16) float blk[];   // [nodes][16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cg = lane & 3;
+  // work item = (tile, part): crowded tiles (few tiles, many points: small grids in low dimension) are shared by `parts` CTAs
+  for (int64_t wk = blockIdx.x; wk < (int64_t)tl.ntiles * parts; wk += gridDim.x) {
+    const int tile = (int)(wk / parts), part = (int)(wk % parts);
+    const int t0 = off[tile], tn = off[tile + 1] - t0;
+    const int p0 = t0 + (int)((int64_t)tn * part / parts), p1 = t0 + (int)((int64_t)tn * (part + 1) / parts);
+    if (p0 == p1) continue;
+    const SkiBlock<D> b = ski_block_of<D>(tile, g, tl);
+    __syncthreads();
+    for (int e = tid; e < b.nodes * 4; e += 256) reinterpret_cast<float4*>(blk)[e] = make_float4(0, 0, 0, 0);
+    __syncthreads();
+    for (int p = p0 + warp; p < p1; p += 8) {
+      int fr[D];
+      float wr[D * 4];
+#pragma unroll
+      for (int i = 0; i < D; ++i) fr[i] = first_s[(int64_t)p * D + i];
+#pragma unroll
+      for (int i = 0; i < D * 4; ++i) wr[i] = wts_s[(int64_t)p * D * 4 + i];
+      const float4 v = reinterpret_cast<const float4*>(V16 + (int64_t)perm[p] * TP)[cg];
+      for (int q = lane >> 2; q < NNZ; q += 8) {
+        int node;
+        float w;
+        ski_local_nnz<D>(fr, wr, b, q, node, w);
+        if (w != 0.f) {
+          float* dst = blk + node * TP + cg * 4;
+          atomicAdd(dst + 0, w * v.x); atomicAdd(dst + 1, w * v.y); atomicAdd(dst + 2, w * v.z); atomicAdd(dst + 3, w * v.w);
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < b.nodes * 4; e += 256) {
+      const float4 x = reinterpret_cast<const float4*>(blk)[e];
+      if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f)
+        red_add_v4(U + ski_block_global<D>(b, g, e >> 2) * TP + (e & 3) * 4, x);
+    }
   }
 }
 
-// out[r][c4] = sum_p w_p U[idx_p][c4]: thread = (row, float4 column group)
+// out[perm[p]] = sum_q w_q U[node_q]: the tile's node block is staged in shared memory once
 template <int D>
-__global__ void ski_gather_kernel(const int* __restrict__ first, const float* __restrict__ wts, SkiGeom g, const float* __restrict__ U,
-                                  int64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+ski_gather_tiled_kernel(const int* __restrict__ first_s, const float* __restrict__ wts_s, const int* __restrict__ perm,
+                        const int* __restrict__ off, SkiGeom g, SkiTiles tl, int parts, const float* __restrict__ U,
+                        float* __restrict__ out) {
   constexpr int NNZ = 1 << (2 * D);
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t r = e >> 2;
-  if (r >= n) return;
-  const int cg = (int)(e & 3);
-  int fr[D];
-  float wr[D * 4];
+  extern __shared__ __align__(16) float blk[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cg = lane & 3;
+  // work item = (tile, part): crowded tiles (few tiles, many points: small grids in low dimension) are shared by `parts` CTAs
+  for (int64_t wk = blockIdx.x; wk < (int64_t)tl.ntiles * parts; wk += gridDim.x) {
+    const int tile = (int)(wk / parts), part = (int)(wk % parts);
+    const int t0 = off[tile], tn = off[tile + 1] - t0;
+    const int p0 = t0 + (int)((int64_t)tn * part / parts), p1 = t0 + (int)((int64_t)tn * (part + 1) / parts);
+    if (p0 == p1) continue;
+    const SkiBlock<D> b = ski_block_of<D>(tile, g, tl);
+    __syncthreads();
+    for (int e = tid; e < b.nodes * 4; e += 256)
+      reinterpret_cast<float4*>(blk)[e] = __ldg(reinterpret_cast<const float4*>(U + ski_block_global<D>(b, g, e >> 2) * TP) + (e & 3));
+    __syncthreads();
+    for (int p = p0 + warp; p < p1; p += 8) {
+      int fr[D];
+      float wr[D * 4];
 #pragma unroll
-  for (int i = 0; i < D; ++i) fr[i] = first[r * D + i];
+      for (int i = 0; i < D; ++i) fr[i] = first_s[(int64_t)p * D + i];
 #pragma unroll
-  for (int i = 0; i < D * 4; ++i) wr[i] = wts[r * D * 4 + i];
-  float4 acc = make_float4(0, 0, 0, 0);
-#pragma unroll 4
-  for (int pnz = 0; pnz < NNZ; ++pnz) {
-    int64_t idx;
-    float w;
-    ski_nnz<D>(fr, wr, g, pnz, idx, w);
-    const float4 u = __ldg(reinterpret_cast<const float4*>(U + idx * TP) + cg);
-    acc.x = fmaf(w, u.x, acc.x); acc.y = fmaf(w, u.y, acc.y); acc.z = fmaf(w, u.z, acc.z); acc.w = fmaf(w, u.w, acc.w);
+      for (int i = 0; i < D * 4; ++i) wr[i] = wts_s[(int64_t)p * D * 4 + i];
+      float4 acc = make_float4(0, 0, 0, 0);
+      for (int q = lane >> 2; q < NNZ; q += 8) {
+        int node;
+        float w;
+        ski_local_nnz<D>(fr, wr, b, q, node, w);
+        const float4 u = *reinterpret_cast<const float4*>(blk + node * TP + cg * 4);
+        acc.x = fmaf(w, u.x, acc.x); acc.y = fmaf(w, u.y, acc.y); acc.z = fmaf(w, u.z, acc.z); acc.w = fmaf(w, u.w, acc.w);
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {   // lanes with the same column group: fixed tree => deterministic
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (lane < 4) reinterpret_cast<float4*>(out + (int64_t)perm[p] * TP)[cg] = acc;
+    }
   }
-  reinterpret_cast<float4*>(out)[r * 4 + cg] = acc;
 }
 
 // mode product: tensor viewed as [outer][G][inner] (inner includes the 16 columns): out[o][i][x] = sum_k T[i][k] in[o][k][x].
@@ -198,20 +346,116 @@ ski_mode_kernel(const float* __restrict__ T, int G, const float* __restrict__ in
 
 // T_i[a][b] = k_1d(|a - b| step_i / l_i): per-dimension factor of the grid covariance (grid_kernel.py:138-157 evaluates the base
 // kernel on every dimension separately, last_dim_is_batch=True)
-__global__ void ski_toeplitz_kernel(float* __restrict__ T, int G, float step, float inv_ls, int kind) {
+__global__ void ski_toeplitz_kernel(float* __restrict__ T, int G, float step, float inv_ls, int kind, int deriv) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= G * G) return;
   const int a = e / G, b = e % G;
   const float r = fabsf((float)(a - b)) * step * inv_ls;   // |dx| / l
   float v;
-  if (kind == GP_RBF) v = expf(-0.5f * r * r);
-  else {
+  if (kind == GP_RBF) {
+    v = expf(-0.5f * r * r);
+    if (deriv) v *= r * r;                                 // l dk/dl = r^2 k  (functions/rbf_covariance.py:20-29)
+  } else {
     const float nu2 = (kind == GP_MATERN12) ? 1.f : (kind == GP_MATERN32 ? 3.f : 5.f);
     const float rho = sqrtf(nu2) * r;
     const float ex = expf(-rho);
-    v = (kind == GP_MATERN12) ? ex : (kind == GP_MATERN32 ? (1.f + rho) * ex : (1.f + rho + rho * rho * (1.f / 3.f)) * ex);
-  }
+    if (!deriv) v = (kind == GP_MATERN12) ? ex : (kind == GP_MATERN32 ? (1.f + rho) * ex : (1.f + rho + rho * rho * (1.f / 3.f)) * ex);
+    else        v = (kind == GP_MATERN12) ? rho * ex : (kind == GP_MATERN32 ? rho * rho * ex : (1.f + rho) * rho * rho * (1.f / 3.f) * ex);
+  }                                                        // l dk/dl = -rho dk/drho  (functions/matern_covariance.py:27-56)
   T[e] = v;
+}
+
+// <a, b> over n floats -> one fp64 partial per CTA (fixed order inside the CTA and on the host: reproducible)
+__global__ void __launch_bounds__(256) ski_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n4,
+                                                      double* __restrict__ part) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    acc += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
+static SkiTiles ski_tiles_of(const gp_ski_state* s, int d) {
+  SkiTiles tl;
+  tl.ntiles = s->ntiles;
+  for (int i = 0; i < SKI_MAXD; ++i) { tl.E[i] = i < d ? s->tile_edge[i] : 1; tl.nt[i] = i < d ? s->tile_num[i] : 1; }
+  return tl;
+}
+
+// bucket the points by tile (counting sort on the device): once per data update
+static int ski_bucket_points(gp_plan* p, const SkiGeom& g) {
+  gp_ski_state* s = p->ski;
+  cudaStream_t st = p->stream;
+  const int d = g.d;
+  const int64_t n = p->n1;
+  GP_REQUIRE(n < ((int64_t)1 << 31), GP_E_SHAPE, "SKI: n too large");
+  static const int edge_by_d[SKI_MAXD + 1] = {0, 256, 32, 8, 3};   // (E + 3)^d nodes x 64 B <= 85 KB of shared memory
+  int64_t nt = 1;
+  for (int i = 0; i < d; ++i) {
+    s->tile_edge[i] = edge_by_d[d];
+    s->tile_num[i] = std::max(1, (int)cdiv(g.G[i] - 3, s->tile_edge[i]));
+    nt *= s->tile_num[i];
+  }
+  GP_REQUIRE(nt <= (1 << 20), GP_E_SHAPE, "SKI: %lld point tiles (grid too fine for d=%d)", (long long)nt, d);
+  s->ntiles = (int)nt;
+  const SkiTiles tl = ski_tiles_of(s, d);
+  GP_CHECK(s->tile_cnt.ensure(sizeof(int) * nt));
+  GP_CHECK(s->tile_off.ensure(sizeof(int) * (nt + 1)));
+  GP_CHECK(s->perm.ensure(sizeof(int) * n));
+  GP_CHECK(s->first_s.ensure(sizeof(int) * n * d));
+  GP_CHECK(s->wts_s.ensure(sizeof(float) * n * d * 4));
+  GP_CUDA(cudaMemsetAsync(s->tile_cnt.p, 0, sizeof(int) * nt, st));
+  const unsigned gb = (unsigned)cdiv(n, 256);
+  int* cnt = s->tile_cnt.as<int>();
+  int* off = s->tile_off.as<int>();
+#define GP_SKI_BUCKET(DD)                                                                                                   \
+  case DD:                                                                                                                  \
+    ski_tile_count_kernel<DD><<<gb, 256, 0, st>>>(s->first.as<int>(), n, tl, cnt);                                          \
+    ski_tile_scan_kernel<<<1, 1024, 0, st>>>(cnt, (int)nt, off);                                                            \
+    ski_tile_fill_kernel<DD><<<gb, 256, 0, st>>>(s->first.as<int>(), s->wts.as<float>(), n, tl, off, cnt, s->perm.as<int>(), \
+                                                 s->first_s.as<int>(), s->wts_s.as<float>());                               \
+    break;
+  switch (d) {
+    GP_SKI_BUCKET(1)
+    GP_SKI_BUCKET(2)
+    GP_SKI_BUCKET(3)
+    GP_SKI_BUCKET(4)
+  }
+#undef GP_SKI_BUCKET
+  p->launches += 3;
+  GP_CUDA(cudaGetLastError());
+  return GP_OK;
+}
+
+constexpr int SKI_TILE_SMEM = 96 * 1024;
+template <int D>
+static int ski_tiled_attrs(gp_plan* p) {
+  static bool done[64] = {};
+  if (!done[p->device & 63]) {
+    GP_CUDA(cudaFuncSetAttribute(ski_scatter_tiled_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKI_TILE_SMEM));
+    GP_CUDA(cudaFuncSetAttribute(ski_gather_tiled_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKI_TILE_SMEM));
+    done[p->device & 63] = true;
+  }
+  return GP_OK;
+}
+// CTAs per tile: ~1024 points each on average (no host read-back of the real counts: the split only balances load)
+static int ski_tile_parts(const gp_plan* p) {
+  const int64_t avg = p->n1 / std::max(1, p->ski->ntiles);
+  return (int)std::min<int64_t>(256, std::max<int64_t>(1, cdiv(avg, 1024)));
+}
+// shared memory of one tile's node block
+static size_t ski_tile_smem(const gp_ski_state* s, int d) {
+  size_t nodes = 1;
+  for (int i = 0; i < d; ++i) nodes *= (size_t)std::min(s->tile_edge[i] + 3, s->G[i]);
+  return nodes * TP * sizeof(float);
 }
 
 int ski_pack(gp_plan* p) {
@@ -237,14 +481,17 @@ int ski_pack(gp_plan* p) {
   GP_CUDA(cudaMemsetAsync(s->flag.p, 0, sizeof(int), st));
   ski_interp_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(p->X1, n, p->ld1, g, s->first.as<int>(), s->wts.as<float>(), s->flag.as<int>());
   p->launches++;
+  GP_CHECK(ski_bucket_points(p, g));
   size_t toff = 0;
   for (int i = 0; i < d; ++i) toff += (size_t)s->G[i] * s->G[i];
   GP_CHECK(s->T.ensure(sizeof(float) * toff));
+  GP_CHECK(s->dT.ensure(sizeof(float) * toff));   // l_i dT_i/dl_i: the factors of the hyper-parameter gradients
   toff = 0;
   for (int i = 0; i < d; ++i) {
     const float l = (p->ls.size() == 1) ? p->ls[0] : p->ls[i];
-    ski_toeplitz_kernel<<<(unsigned)cdiv((int64_t)s->G[i] * s->G[i], 256), 256, 0, st>>>(s->T.as<float>() + toff, s->G[i], s->step[i], 1.f / l, p->kind);
-    p->launches++;
+    ski_toeplitz_kernel<<<(unsigned)cdiv((int64_t)s->G[i] * s->G[i], 256), 256, 0, st>>>(s->T.as<float>() + toff, s->G[i], s->step[i], 1.f / l, p->kind, 0);
+    ski_toeplitz_kernel<<<(unsigned)cdiv((int64_t)s->G[i] * s->G[i], 256), 256, 0, st>>>(s->dT.as<float>() + toff, s->G[i], s->step[i], 1.f / l, p->kind, 1);
+    p->launches += 2;
     toff += (size_t)s->G[i] * s->G[i];
   }
   int h_oob = 0;
@@ -269,11 +516,18 @@ static int ski_matmul_d(gp_plan* p, const float* V16, int t, float* OUT16) {
   g.d = D;
   g.M = 1;
   for (int i = D - 1; i >= 0; --i) { g.G[i] = s->G[i]; g.lo[i] = s->lo[i]; g.step[i] = s->step[i]; g.stride[i] = g.M; g.M *= s->G[i]; }
-  constexpr int NNZ = 1 << (2 * D);
+  (void)t;
+  (void)n;
   float* A = s->gridA.as<float>();
   float* B = s->gridB.as<float>();
+  const SkiTiles tl = ski_tiles_of(s, D);
+  const size_t tsm = ski_tile_smem(s, D);
+  GP_REQUIRE(tsm <= (size_t)SKI_TILE_SMEM, GP_E_SHAPE, "SKI: tile block of %zu bytes does not fit in shared memory", tsm);
+  GP_CHECK(ski_tiled_attrs<D>(p));
+  const int parts = ski_tile_parts(p);
+  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 4 * (int64_t)p->n_sm);
   GP_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * g.M * TP, st));
-  ski_scatter_kernel<D><<<(unsigned)cdiv(n * NNZ, 256), 256, 0, st>>>(s->first.as<int>(), s->wts.as<float>(), g, V16, n, (t + 3) / 4, A);
+  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, V16, A);
   size_t toff = 0;
   float* cur = A;
   float* nxt = B;
@@ -287,10 +541,89 @@ static int ski_matmul_d(gp_plan* p, const float* V16, int t, float* OUT16) {
     toff += (size_t)G * G;
     std::swap(cur, nxt);
   }
-  ski_gather_kernel<D><<<(unsigned)cdiv(n * 4, 256), 256, 0, st>>>(s->first.as<int>(), s->wts.as<float>(), g, cur, n, OUT16);
+  ski_gather_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, cur, OUT16);
   p->launches += 2 + D;
   GP_CUDA(cudaGetLastError());
   return GP_OK;
+}
+
+// Bilinear derivative of the interpolated operator (the reference reaches it through InterpolatedLinearOperator._bilinear_derivative
+// -> the grid kernel's Toeplitz columns -> autograd, kernels/grid_kernel.py:138-177):
+//   sum_ij (L_i . R_j) d(K_ski)_ij / d theta = < A, dK_uu/d theta B >,   A = W^T L, B = W^T R   (grid blocks [M][16]),
+//   dK_uu / d l_i = (1 / l_i) T_0 x ... x (l_i dT_i/dl_i) x ... x T_{d-1}.
+// total[0] += <A, K_uu B> (d/d outputscale), total[1 + i] += <A, (.. dT_i ..) B>: d + 1 sweeps of d mode products each.
+template <int D>
+static int ski_bilinear_d(gp_plan* p, const float* L16, const float* R16, double* total) {
+  gp_ski_state* s = p->ski;
+  cudaStream_t st = p->stream;
+  const int64_t n = p->n1;
+  SkiGeom g;
+  g.d = D;
+  g.M = 1;
+  for (int i = D - 1; i >= 0; --i) { g.G[i] = s->G[i]; g.lo[i] = s->lo[i]; g.step[i] = s->step[i]; g.stride[i] = g.M; g.M *= s->G[i]; }
+  (void)n;
+  constexpr int DOT_BLOCKS = 296;
+  const SkiTiles tl = ski_tiles_of(s, D);
+  const size_t tsm = ski_tile_smem(s, D);
+  GP_CHECK(ski_tiled_attrs<D>(p));
+  const int parts = ski_tile_parts(p);
+  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 4 * (int64_t)p->n_sm);
+  GP_CHECK(s->gridC.ensure(sizeof(float) * g.M * TP));
+  GP_CHECK(s->gridD.ensure(sizeof(float) * g.M * TP));
+  GP_CHECK(p->misc.ensure(sizeof(double) * DOT_BLOCKS * (D + 1)));
+  float* A = s->gridC.as<float>();
+  float* B = s->gridD.as<float>();
+  double* part = p->misc.as<double>();
+  GP_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * g.M * TP, st));
+  GP_CUDA(cudaMemsetAsync(B, 0, sizeof(float) * g.M * TP, st));
+  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, L16, A);
+  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, R16, B);
+  p->launches += 2;
+  for (int term = 0; term <= D; ++term) {          // term 0: K_uu ; term 1 + i: derivative factor in dimension i
+    size_t toff = 0;
+    const float* cur = B;
+    float* bufs[2] = {s->gridA.as<float>(), s->gridB.as<float>()};
+    for (int i = 0; i < D; ++i) {
+      const int G = s->G[i];
+      const int64_t inner = g.stride[i] * TP;
+      const int64_t tot = g.M / G * TP;
+      const int64_t nslab = cdiv(tot, SKI_MT);
+      const size_t sh = sizeof(float) * ((size_t)G * (G + 1) + 4 + (size_t)G * SKI_MT);
+      const float* Tm = ((term == 1 + i) ? s->dT.as<float>() : s->T.as<float>()) + toff;
+      float* out = bufs[i & 1];
+      ski_mode_kernel<<<(unsigned)std::min<int64_t>(nslab, 8 * p->n_sm), 256, sh, st>>>(Tm, G, cur, out, inner, tot, nslab);
+      cur = out;
+      toff += (size_t)G * G;
+    }
+    ski_dot_kernel<<<DOT_BLOCKS, 256, 0, st>>>(A, cur, g.M * TP / 4, part + (size_t)term * DOT_BLOCKS);
+    p->launches += D + 1;
+  }
+  GP_CUDA(cudaGetLastError());
+  std::vector<double> h((size_t)DOT_BLOCKS * (D + 1));
+  GP_CUDA(cudaMemcpyAsync(h.data(), part, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(cudaStreamSynchronize(st));
+  for (int term = 0; term <= D; ++term) {
+    double acc = 0.0;
+    for (int b = 0; b < DOT_BLOCKS; ++b) acc += h[(size_t)term * DOT_BLOCKS + b];
+    total[term] += acc;
+  }
+  return GP_OK;
+}
+
+int ski_bilinear(gp_plan* p, const float* L16, const float* R16, double* total) {
+  static bool attr_done[64] = {};
+  if (!attr_done[p->device & 63]) {
+    GP_CUDA(cudaFuncSetAttribute(ski_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    attr_done[p->device & 63] = true;
+  }
+  switch (p->d) {
+    case 1: return ski_bilinear_d<1>(p, L16, R16, total);
+    case 2: return ski_bilinear_d<2>(p, L16, R16, total);
+    case 3: return ski_bilinear_d<3>(p, L16, R16, total);
+    case 4: return ski_bilinear_d<4>(p, L16, R16, total);
+  }
+  set_error("SKI backend supports 1 <= d <= 4 (d=%d)", p->d);
+  return GP_E_SHAPE;
 }
 
 // partial[0][r][:] = (W K_uu W^T V16)[r][:]   (outputscale / noise are applied by the finish kernels)

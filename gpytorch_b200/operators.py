@@ -36,17 +36,18 @@ _PLAN_CACHE_MAX = 64          # a batch of 16 independent operators (+ their cro
 _PLAN_LOCK = __import__("threading").RLock()   # BatchLinearOperator drives the cache from worker threads
 
 
-def _get_plan(x1, x2, backend, row_begin, row_count, comm) -> Plan:
+def _get_plan(x1, x2, backend, row_begin, row_count, comm, slot=0) -> Plan:
     if not x1.is_cuda:
         raise RuntimeError("x1 must live on a CUDA device: gpytorch_b200 has no CPU path")
     with _PLAN_LOCK:
-        return _get_plan_locked(x1, x2, backend, row_begin, row_count, comm)
+        return _get_plan_locked(x1, x2, backend, row_begin, row_count, comm, slot)
 
 
-def _get_plan_locked(x1, x2, backend, row_begin, row_count, comm) -> Plan:
-    # a plan enqueues on the stream that was current when it was created: the stream is part of the identity
+def _get_plan_locked(x1, x2, backend, row_begin, row_count, comm, slot=0) -> Plan:
+    # a plan enqueues on the stream that was current when it was created: the stream is part of the identity; so is the slot:
+    # the terms of a kernel sum over the SAME inputs need one plan each (each holds its own packed lengthscales)
     key = (x1.data_ptr(), tuple(x1.shape), x1.stride(0), None if x2 is None else (x2.data_ptr(), tuple(x2.shape), x2.stride(0)),
-           backend, str(x1.device), row_begin, row_count, id(comm), torch.cuda.current_stream(x1.device).cuda_stream)
+           backend, str(x1.device), row_begin, row_count, id(comm), torch.cuda.current_stream(x1.device).cuda_stream, slot)
     plan = _PLAN_CACHE.pop(key, None)
     src_versions = (x1._version, None if x2 is None else x2._version)
     if plan is not None and plan._src_versions != src_versions:
@@ -151,7 +152,7 @@ class KernelLinearOperator:
         fresh = False
         if self._plan is None:
             self._plan = _get_plan(self.x1, None if self.same else self.x2, settings.backend.value(),
-                                   self._row_begin, self._row_count, self._comm)
+                                   self._row_begin, self._row_count, self._comm, getattr(self, "_plan_slot", 0))
             fresh = True
         if torch.is_tensor(noise):
             ls, os_, nz, _ = self._host_hypers(noise)
@@ -276,7 +277,10 @@ class KernelLinearOperator:
     def __add__(self, other):
         if isinstance(other, (ConstantDiagLinearOperator, DiagLinearOperator)):
             return AddedDiagLinearOperator(self, other)
-        raise NotImplementedError("KernelLinearOperator only adds a (Constant)DiagLinearOperator")
+        if isinstance(other, KernelLinearOperator) and not isinstance(other, SKIKernelLinearOperator) \
+                and not isinstance(self, SKIKernelLinearOperator):
+            return SumKernelLinearOperator([self, other])     # K_1 + K_2 stays lazy: one engine operator (csrc/sum.cu)
+        raise NotImplementedError("a kernel operator adds a (Constant)DiagLinearOperator or another kernel operator")
 
     def add_jitter(self, jitter_val=1e-3):
         return AddedDiagLinearOperator(self, ConstantDiagLinearOperator(torch.tensor(jitter_val, device=self.device), self.shape[0]))
@@ -304,7 +308,13 @@ class SumKernelLinearOperator(KernelLinearOperator):
         for o in flat[1:]:
             if o.shape != first.shape or o.same != first.same:
                 raise RuntimeError(f"cannot add kernels of shapes {tuple(first.shape)} and {tuple(o.shape)}")
-        self.ops = flat
+        # one engine plan per term even when the terms see the same inputs: re-wrap (the caller's operators stay usable on their
+        # own) and give every term its own slot of the plan cache
+        self.ops = []
+        for i, o in enumerate(flat):
+            t = KernelLinearOperator(o.x1, o.x2, o.kind, o.lengthscale, o.outputscale, comm=o._comm, row_begin=o._row_begin, row_count=o._row_count)
+            t._plan_slot = 1 + i
+            self.ops.append(t)
         self.x1, self.x2, self.same = first.x1, first.x2, first.same
         self.kind = "sum"
         self.lengthscale, self.outputscale = first.lengthscale, first.outputscale   # representative only (device / dtype)
@@ -593,6 +603,8 @@ class AddedDiagLinearOperator:
         n = self.shape[0]
         if settings.max_preconditioner_size.value() == 0 or n < settings.min_preconditioning_size.value():
             return None, None, 0.0
+        if isinstance(self.kernel_op, SKIKernelLinearOperator):
+            return None, None, 0.0      # the reference's interpolated operator has no pivoted-Cholesky preconditioner either
         if self._precond_cache is None:
             p = self._plan()
             lt, piv, st = p.pivoted_cholesky(settings.max_preconditioner_size.value(), settings.preconditioner_tolerance.value())

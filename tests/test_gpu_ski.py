@@ -1,5 +1,7 @@
 """GPU parity of the SKI / KISS-GP backend (csrc/ski.cu; BASELINE configs[4]) against the pinned CPU
 oracle (oracle/ski.py: interpolation checked against outputs of the reference's own code, tests/golden/ski_golden.npz).
+Hyper-parameter gradients (gp_bilinear_grad on the SKI backend: < W^T L, dK_uu/dtheta W^T R > on the grid) against fp64 autograd
+through the oracle's interpolated product.
 Tolerances: products rel-l2 <= 2e-5 (fp32 interpolation weights and mode products, atomics in arbitrary order; the oracle runs in
 fp64), MLL by the Krylov rule of tests/test_gpu_configs.py."""
 import math
@@ -111,3 +113,77 @@ def test_ski_mll_matches_oracle_and_api(cuda_dev):
     alpha = torch.cholesky_solve(y.double().unsqueeze(-1), Lc)[:, 0]
     exact = -0.5 * (float(y.double() @ alpha) + float(2 * Lc.diagonal().log().sum()) + n * math.log(2 * math.pi)) / n
     assert abs(out.item() - exact) < 0.03 * abs(exact) + 2e-3
+
+
+@pytest.mark.parametrize("kind,d,sizes,ard", [("rbf", 2, [24, 18], False), ("matern52", 3, [14, 12, 10], False), ("matern32", 2, [20, 20], True),
+                                               ("matern12", 1, [40], False)])
+def test_ski_bilinear_derivative_matches_oracle_autograd(cuda_dev, kind, d, sizes, ard):
+    from gpytorch_b200.engine import Plan
+
+    g = torch.Generator().manual_seed(11 + d)
+    n, s_cols = 2000, 19                                  # 19 columns: two sweeps of 16
+    axes, lo, step = _grid(sizes, [(0.0, 1.0)] * d)
+    x = torch.rand(n, d, generator=g)
+    left = torch.randn(n, s_cols, generator=g)
+    right = torch.randn(n, s_cols, generator=g)
+    ls0 = [0.3 + 0.1 * i for i in range(d)] if ard else [0.35]
+    ls = torch.tensor(ls0, dtype=torch.float64, requires_grad=True)
+    osc = torch.tensor(1.6, dtype=torch.float64, requires_grad=True)
+    val = (left.double() * ski.ski_matmul(kind, x.double(), [a.double() for a in axes], ls, osc, right.double())).sum()
+    val.backward()
+    p = Plan(x.to(cuda_dev)).set_ski(sizes, lo, step).set_hypers(kind, ls0, 1.6, 0.1)
+    gl, go = p.bilinear_grad(left.to(cuda_dev), right.to(cuda_dev))
+    scale = max(abs(float(v)) for v in ls.grad) + 1e-12
+    assert go == pytest.approx(osc.grad.item(), rel=2e-4, abs=2e-4 * abs(val.item()))
+    for a, b in zip(gl, ls.grad.tolist()):
+        assert a == pytest.approx(b, rel=5e-4, abs=5e-4 * scale)
+    p.close()
+
+
+def test_ski_training_step_through_the_api(cuda_dev):
+    """One optimiser-style step on ScaleKernel(GridInterpolationKernel(RBFKernel())): loss and gradients of lengthscale / outputscale /
+    noise against dense fp64 autograd on the oracle's K_ski (stochastic trace estimate: ~15 %)."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    n, d, sizes, ls0, os0, nz0 = 2000, 2, [26, 26], 0.3, 1.2, 0.25
+    x, y = om.synthetic_problem(n, d, 6, torch.float32)
+    axes, lo, step = _grid(sizes, [(0.0, 1.0)] * d)
+    lik = gp.likelihoods.GaussianLikelihood().to(cuda_dev)
+    lik.noise = nz0
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(x.to(cuda_dev), y.to(cuda_dev), lik)
+            self.mean_module = gp.means.ZeroMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.GridInterpolationKernel(gp.kernels.RBFKernel(), grid_size=26, num_dims=2,
+                                                                                       grid_bounds=[(0.0, 1.0)] * 2))
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.base_kernel.lengthscale = ls0
+    model.covar_module.outputscale = os0
+    model.train(); lik.train()
+    with settings.probe_seed(5), settings.cg_tolerance(1e-3), settings.num_trace_samples(15):
+        loss = -gp.mlls.ExactMarginalLogLikelihood(lik, model)(model(x.to(cuda_dev)), y.to(cuda_dev))
+        loss.backward()
+    ls = torch.tensor(ls0, dtype=torch.float64, requires_grad=True)
+    osc = torch.tensor(os0, dtype=torch.float64, requires_grad=True)
+    nz = torch.tensor(nz0, dtype=torch.float64, requires_grad=True)
+    Kd = ski.ski_matmul("rbf", x.double(), [a.double() for a in axes], ls, osc, torch.eye(n, dtype=torch.float64))
+    Kd = 0.5 * (Kd + Kd.t()) + nz * torch.eye(n, dtype=torch.float64)
+    Lc = torch.linalg.cholesky(Kd)
+    r = y.double().unsqueeze(-1)
+    ref = 0.5 * ((r * torch.cholesky_solve(r, Lc)).sum() + 2 * Lc.diagonal().log().sum() + n * math.log(2 * math.pi)) / n
+    ref.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=3e-2, abs=2e-3)
+    k = model.covar_module
+
+    def raw_grad(p):
+        return p.grad.item() / torch.sigmoid(p).item()
+
+    assert raw_grad(k.base_kernel.base_kernel.raw_lengthscale) == pytest.approx(ls.grad.item(), rel=0.2, abs=3e-3)
+    assert raw_grad(k.raw_outputscale) == pytest.approx(osc.grad.item(), rel=0.2, abs=3e-3)
+    assert raw_grad(lik.raw_noise) == pytest.approx(nz.grad.item(), rel=0.2, abs=3e-3)

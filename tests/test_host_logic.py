@@ -265,10 +265,42 @@ def test_operator_protocol_without_compute():
     with pytest.raises(RuntimeError, match="square"):
         AddedDiagLinearOperator(cr, ConstantDiagLinearOperator(torch.tensor(0.1), 30))
     with pytest.raises(NotImplementedError):
-        sq + sq
+        sq + 1.0
     with pytest.raises(RuntimeError):      # products need the CUDA engine: no CPU fallback
         sq.matmul(torch.rand(30, 2))
     assert gp.settings.fast_pred_var.off() and gp.settings.skip_posterior_variances.off()
     with gp.settings.fast_pred_var(True), gp.settings.skip_posterior_variances(True):
         assert gp.settings.fast_pred_var.on() and gp.settings.skip_posterior_variances.on()
     assert gp.settings.fast_pred_var.off()
+
+
+def test_additive_kernel_protocol_without_compute():
+    """k1 + k2 -> AdditiveKernel with nested sums flattened (kernels/kernel.py:541-545, :592-621); calling it gives ONE lazy sum
+    operator whose terms keep their own active dimensions; slicing / transposing / adding the noise stay lazy."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200.operators import AddedDiagLinearOperator, ConstantDiagLinearOperator, SumKernelLinearOperator
+
+    k = gp.kernels.ScaleKernel(gp.kernels.RBFKernel(active_dims=[0, 2])) + gp.kernels.ScaleKernel(gp.kernels.MaternKernel(nu=1.5))
+    assert isinstance(k, gp.kernels.AdditiveKernel) and len(k.kernels) == 2
+    assert len((k + gp.kernels.RBFKernel()).kernels) == 3 and len((gp.kernels.RBFKernel() + k).kernels) == 3
+    names = sorted(n for n, _ in k.named_parameters())
+    assert names == ["kernels.0.base_kernel.raw_lengthscale", "kernels.0.raw_outputscale",
+                     "kernels.1.base_kernel.raw_lengthscale", "kernels.1.raw_outputscale"]
+    x = torch.rand(40, 3)
+    op = k(x)
+    assert isinstance(op, SumKernelLinearOperator) and [o.kind for o in op.ops] == ["rbf", "matern32"]
+    assert op.ops[0].x1.shape == (40, 2) and op.ops[1].x1.shape == (40, 3) and op.shape == torch.Size([40, 40]) and op.same
+    assert len(op.hyper_tensors()) == 4 and op.requires_grad and not op.detach().requires_grad
+    sub = op[5:, :7]
+    assert isinstance(sub, SumKernelLinearOperator) and sub.shape == torch.Size([35, 7]) and sub.t().shape == torch.Size([7, 35])
+    khat = op + ConstantDiagLinearOperator(torch.tensor(0.1), 40)
+    assert isinstance(khat, AddedDiagLinearOperator) and khat.kernel_op is op
+    # operator-level addition gives the same lazy sum, nested sums are flattened, five terms are refused
+    a = op.ops[0]
+    assert len((a + a).ops) == 2 and len(((a + a) + (a + a)).ops) == 4
+    with pytest.raises(RuntimeError, match="1 to 4 terms"):
+        (a + a) + (a + a) + a
+    with pytest.raises(RuntimeError, match="cannot add kernels of shapes"):
+        a + a[:10]
+    with pytest.raises(RuntimeError, match="must be kernels"):
+        gp.kernels.AdditiveKernel(gp.kernels.RBFKernel(), 3.0)
