@@ -590,7 +590,10 @@ int mbcg_run(gp_plan* p, const float* RHS, int64_t ldr, int t, int n_tridiag, fl
   const bool precond = W != nullptr;
   if (!precond) k = 0;
   const int wp = precond ? w_pitch(k) : 0;
-  static const int grid_mult = getenv("GP_CG_GRID_MULT") ? std::max(1, atoi(getenv("GP_CG_GRID_MULT"))) : 2;   // CTAs per SM of the row-pass kernels
+  // CTAs per SM of the row-pass kernels: 2 with a preconditioner (the W chunk staged in shared memory bounds residency; 3 or 4
+  // measured no faster at C2), 8 without one (pure streaming over the vectors: N = 10^6 rows at BASELINE C5)
+  static const int grid_mult_env = getenv("GP_CG_GRID_MULT") ? std::max(1, atoi(getenv("GP_CG_GRID_MULT"))) : 0;
+  const int grid_mult = grid_mult_env ? grid_mult_env : (precond ? 2 : 8);
   const int G = (int)std::min<int64_t>(cdiv(n, CG_ROWS), (int64_t)grid_mult * p->n_sm);
   const int L1 = TP + k * TP;           // message 1: pV | W^T V
   const float* dvec = p->noise_diag ? p->noise_diag + p->row_begin : nullptr;

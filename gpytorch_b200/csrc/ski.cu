@@ -175,40 +175,78 @@ __device__ __forceinline__ SkiBlock<D> ski_block_of(int tile, const SkiGeom& g, 
   b.nodes = pch;
   return b;
 }
-// block-local node -> flat index into the global grid block
-template <int D>
-__device__ __forceinline__ int64_t ski_block_global(const SkiBlock<D>& b, const SkiGeom& g, int node) {
-  int64_t idx = 0;
+// Row-wise traversal of a tile's node block for the exchanges with the global grid block: a "row" fixes the coordinates of
+// dimensions 0 .. D-2 (one division chain per row instead of one per element), the lanes cover (last-dimension node, column
+// group) pairs, 8 nodes x 4 groups per pass.  fn(local node, global flat index, column group).
+template <int D, typename F>
+__device__ __forceinline__ void ski_block_rows(const SkiBlock<D>& b, const SkiGeom& g, int warp, int nwarps, int lane, F fn) {
+  const int last = b.ext[D - 1];
+  const int nrows = b.nodes / last;
+  for (int row = warp; row < nrows; row += nwarps) {
+    int rem = row, node0 = 0;
+    int64_t idx0 = (int64_t)b.base[D - 1] * g.stride[D - 1];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    const int c = node / b.pitch[i];
-    node -= c * b.pitch[i];
-    idx += (int64_t)(b.base[i] + c) * g.stride[i];
+    for (int i = D - 2; i >= 0; --i) {
+      const int c = rem % b.ext[i];
+      rem /= b.ext[i];
+      node0 += c * b.pitch[i];
+      idx0 += (int64_t)(b.base[i] + c) * g.stride[i];
+    }
+    for (int c = lane >> 2; c < last; c += 8) fn(node0 + c, idx0 + (int64_t)c * g.stride[D - 1], lane & 3);
   }
-  return idx;
 }
-// neighbour p (base-4 digits, dimension 0 most significant) of a point: block-local node and weight
+
+// neighbour q (base-4 digits, dimension 0 most significant) of the warp's current point: block-local node and weight.  The
+// point's 4 D weights live one per lane (lane i * 4 + c holds w_i[c]) and are fetched with shuffles: indexing a per-thread
+// array with the run-time digit would put it in local memory (3 GB of L2 traffic per product at C5 in the first version).
+// fr[i] = first node of the point in dimension i relative to the block.  All 32 lanes must call this together.
 template <int D>
-__device__ __forceinline__ void ski_local_nnz(const int* __restrict__ fr, const float* __restrict__ wr, const SkiBlock<D>& b, int p, int& node, float& w) {
+__device__ __forceinline__ void ski_local_nnz(const int (&fr)[D], float myw, const SkiBlock<D>& b, int q, int& node, float& w) {
   node = 0;
   w = 1.f;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const int c = (p >> (2 * (D - 1 - i))) & 3;
-    node += (fr[i] - b.base[i] + c) * b.pitch[i];
-    w *= wr[i * 4 + c];
+    const int c = (q >> (2 * (D - 1 - i))) & 3;
+    node += (fr[i] + c) * b.pitch[i];
+    w *= __shfl_sync(0xffffffffu, myw, i * 4 + c);
   }
 }
-
-// U += W^T V: one CTA per (tile, part), node block in shared memory; a warp takes a point, its lanes = 8 neighbours x 4 column groups
+// Interpolation data of one sorted point as the warp holds it: lane l < 4 D has weight w_{l / 4}[l % 4], lane l < D the first
+// node of dimension l.  Loaded one point ahead of its use (the loads are dependent -- perm -> V row -- and a tile's points are
+// visited once: without the look-ahead every point costs a full L2 / HBM round trip).
+struct SkiPoint {
+  float w;
+  int f;
+};
 template <int D>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ SkiPoint ski_load_point(const int* __restrict__ first_s, const float* __restrict__ wts_s, int64_t p, int lane) {
+  SkiPoint pt;
+  pt.w = (lane < 4 * D) ? wts_s[p * (4 * D) + lane] : 0.f;
+  pt.f = (lane < D) ? first_s[p * D + lane] : 0;
+  return pt;
+}
+template <int D>
+__device__ __forceinline__ void ski_point_first(const SkiPoint& pt, const SkiBlock<D>& b, int (&fr)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) fr[i] = __shfl_sync(0xffffffffu, pt.f, i) - b.base[i];
+}
+
+// U += W^T V: one CTA (4 warps) per (tile, part), node block in shared memory.  Warp w owns column group w (4 of the 16 columns)
+// of EVERY node of the block and visits every point of the tile: its lanes are 32 of the point's 4^D neighbours, all distinct
+// nodes, so the accumulation is a plain shared-memory read-modify-write -- no atomics (fp32 atomicAdd on shared memory is a
+// compare-and-swap loop on this architecture: ATOMS.CAST.SPIN, 250 cycles per add under contention; the version built on it
+// took 2.0 ms per product at C5).
+constexpr int SKI_SC_THREADS = 128;
+template <int D>
+__global__ void __launch_bounds__(SKI_SC_THREADS)
 ski_scatter_tiled_kernel(const int* __restrict__ first_s, const float* __restrict__ wts_s, const int* __restrict__ perm,
                          const int* __restrict__ off, SkiGeom g, SkiTiles tl, int parts, const float* __restrict__ V16,
                          float* __restrict__ U) {
   constexpr int NNZ = 1 << (2 * D);
-  extern __shared__ __align__(16) float blk[];   // [nodes][16]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cg = lane & 3;
+  constexpr int NIT = (NNZ + 31) / 32;
+  extern __shared__ __align__(16) float blk[];   // [4 column groups][nodes][4]: a warp's 32 lanes (32 nodes, one column group) then
+                                                 // spread over all banks; with [nodes][16] they hit 4 banks (16-way conflicts, 1.3 ms)
+  const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;
   // work item = (tile, part): crowded tiles (few tiles, many points: small grids in low dimension) are shared by `parts` CTAs
   for (int64_t wk = blockIdx.x; wk < (int64_t)tl.ntiles * parts; wk += gridDim.x) {
     const int tile = (int)(wk / parts), part = (int)(wk % parts);
@@ -217,36 +255,55 @@ ski_scatter_tiled_kernel(const int* __restrict__ first_s, const float* __restric
     if (p0 == p1) continue;
     const SkiBlock<D> b = ski_block_of<D>(tile, g, tl);
     __syncthreads();
-    for (int e = tid; e < b.nodes * 4; e += 256) reinterpret_cast<float4*>(blk)[e] = make_float4(0, 0, 0, 0);
+    for (int e = tid; e < b.nodes * 4; e += SKI_SC_THREADS) reinterpret_cast<float4*>(blk)[e] = make_float4(0, 0, 0, 0);
     __syncthreads();
-    for (int p = p0 + warp; p < p1; p += 8) {
+    float* mine = blk + (size_t)cg * b.nodes * 4;   // this warp's plane
+    // two-deep look-ahead: point data and V row of p + 1, permutation entry of p + 2
+    SkiPoint pt = ski_load_point<D>(first_s, wts_s, p0, lane);
+    float4 v = reinterpret_cast<const float4*>(V16 + (int64_t)perm[p0] * TP)[cg];
+    int row_n = (p0 + 1 < p1) ? perm[p0 + 1] : 0;
+    for (int p = p0; p < p1; ++p) {
+      SkiPoint pt_n = pt;
+      float4 v_n = v;
+      int row_nn = 0;
+      if (p + 1 < p1) {
+        pt_n = ski_load_point<D>(first_s, wts_s, p + 1, lane);
+        v_n = reinterpret_cast<const float4*>(V16 + (int64_t)row_n * TP)[cg];
+        if (p + 2 < p1) row_nn = perm[p + 2];
+      }
       int fr[D];
-      float wr[D * 4];
+      ski_point_first<D>(pt, b, fr);
+      int node[NIT];
+      float w[NIT];
 #pragma unroll
-      for (int i = 0; i < D; ++i) fr[i] = first_s[(int64_t)p * D + i];
+      for (int k = 0; k < NIT; ++k) {
+        const int q = lane + 32 * k;
+        ski_local_nnz<D>(fr, pt.w, b, q < NNZ ? q : 0, node[k], w[k]);
+        if (q >= NNZ) w[k] = 0.f;
+      }
+      float4 u[NIT];
 #pragma unroll
-      for (int i = 0; i < D * 4; ++i) wr[i] = wts_s[(int64_t)p * D * 4 + i];
-      const float4 v = reinterpret_cast<const float4*>(V16 + (int64_t)perm[p] * TP)[cg];
-      for (int q = lane >> 2; q < NNZ; q += 8) {
-        int node;
-        float w;
-        ski_local_nnz<D>(fr, wr, b, q, node, w);
-        if (w != 0.f) {
-          float* dst = blk + node * TP + cg * 4;
-          atomicAdd(dst + 0, w * v.x); atomicAdd(dst + 1, w * v.y); atomicAdd(dst + 2, w * v.z); atomicAdd(dst + 3, w * v.w);
+      for (int k = 0; k < NIT; ++k) u[k] = *reinterpret_cast<const float4*>(mine + node[k] * 4);
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        if (w[k] != 0.f) {   // lanes of one instruction hit distinct nodes; lanes with w = 0 (padding, one-hot edge cells) stay away
+          u[k].x = fmaf(w[k], v.x, u[k].x); u[k].y = fmaf(w[k], v.y, u[k].y); u[k].z = fmaf(w[k], v.z, u[k].z); u[k].w = fmaf(w[k], v.w, u[k].w);
+          *reinterpret_cast<float4*>(mine + node[k] * 4) = u[k];
         }
       }
+      __syncwarp();
+      pt = pt_n; v = v_n; row_n = row_nn;
     }
     __syncthreads();
-    for (int e = tid; e < b.nodes * 4; e += 256) {
-      const float4 x = reinterpret_cast<const float4*>(blk)[e];
-      if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f)
-        red_add_v4(U + ski_block_global<D>(b, g, e >> 2) * TP + (e & 3) * 4, x);
-    }
+    ski_block_rows<D>(b, g, cg, SKI_SC_THREADS / 32, lane, [&](int node, int64_t idx, int q4) {
+      const float4 x = reinterpret_cast<const float4*>(blk)[q4 * b.nodes + node];
+      if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) red_add_v4(U + idx * TP + q4 * 4, x);
+    });
   }
 }
 
-// out[perm[p]] = sum_q w_q U[node_q]: the tile's node block is staged in shared memory once
+// out[perm[p]] = sum_q w_q U[node_q]: the tile's node block is staged in shared memory once; a warp takes every 8th point, its
+// lanes = 8 neighbours x 4 column groups
 template <int D>
 __global__ void __launch_bounds__(256)
 ski_gather_tiled_kernel(const int* __restrict__ first_s, const float* __restrict__ wts_s, const int* __restrict__ perm,
@@ -255,7 +312,6 @@ ski_gather_tiled_kernel(const int* __restrict__ first_s, const float* __restrict
   constexpr int NNZ = 1 << (2 * D);
   extern __shared__ __align__(16) float blk[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cg = lane & 3;
-  // work item = (tile, part): crowded tiles (few tiles, many points: small grids in low dimension) are shared by `parts` CTAs
   for (int64_t wk = blockIdx.x; wk < (int64_t)tl.ntiles * parts; wk += gridDim.x) {
     const int tile = (int)(wk / parts), part = (int)(wk % parts);
     const int t0 = off[tile], tn = off[tile + 1] - t0;
@@ -263,21 +319,28 @@ ski_gather_tiled_kernel(const int* __restrict__ first_s, const float* __restrict
     if (p0 == p1) continue;
     const SkiBlock<D> b = ski_block_of<D>(tile, g, tl);
     __syncthreads();
-    for (int e = tid; e < b.nodes * 4; e += 256)
-      reinterpret_cast<float4*>(blk)[e] = __ldg(reinterpret_cast<const float4*>(U + ski_block_global<D>(b, g, e >> 2) * TP) + (e & 3));
+    ski_block_rows<D>(b, g, warp, 8, lane, [&](int node, int64_t idx, int q4) {
+      reinterpret_cast<float4*>(blk)[node * 4 + q4] = __ldg(reinterpret_cast<const float4*>(U + idx * TP) + q4);
+    });
+    // first point of this warp: loaded while the block is being staged
+    SkiPoint pt = {0.f, 0};
+    int row = 0;
+    if (p0 + warp < p1) { pt = ski_load_point<D>(first_s, wts_s, p0 + warp, lane); row = perm[p0 + warp]; }
     __syncthreads();
     for (int p = p0 + warp; p < p1; p += 8) {
+      SkiPoint pt_n = pt;
+      int row_n = row;
+      if (p + 8 < p1) { pt_n = ski_load_point<D>(first_s, wts_s, p + 8, lane); row_n = perm[p + 8]; }
       int fr[D];
-      float wr[D * 4];
-#pragma unroll
-      for (int i = 0; i < D; ++i) fr[i] = first_s[(int64_t)p * D + i];
-#pragma unroll
-      for (int i = 0; i < D * 4; ++i) wr[i] = wts_s[(int64_t)p * D * 4 + i];
+      ski_point_first<D>(pt, b, fr);
       float4 acc = make_float4(0, 0, 0, 0);
-      for (int q = lane >> 2; q < NNZ; q += 8) {
+#pragma unroll 2
+      for (int k = 0; k < (NNZ + 7) / 8; ++k) {        // warp-uniform trip count: the shuffles need all lanes
+        const int q = (lane >> 2) + 8 * k;
         int node;
         float w;
-        ski_local_nnz<D>(fr, wr, b, q, node, w);
+        ski_local_nnz<D>(fr, pt.w, b, q < NNZ ? q : 0, node, w);
+        if (q >= NNZ) w = 0.f;
         const float4 u = *reinterpret_cast<const float4*>(blk + node * TP + cg * 4);
         acc.x = fmaf(w, u.x, acc.x); acc.y = fmaf(w, u.y, acc.y); acc.z = fmaf(w, u.z, acc.z); acc.w = fmaf(w, u.w, acc.w);
       }
@@ -286,60 +349,123 @@ ski_gather_tiled_kernel(const int* __restrict__ first_s, const float* __restrict
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
         acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
       }
-      if (lane < 4) reinterpret_cast<float4*>(out + (int64_t)perm[p] * TP)[cg] = acc;
+      if (lane < 4) reinterpret_cast<float4*>(out + (int64_t)row * TP)[cg] = acc;
+      pt = pt_n; row = row_n;
     }
   }
 }
 
-// mode product: tensor viewed as [outer][G][inner] (inner includes the 16 columns): out[o][i][x] = sum_k T[i][k] in[o][k][x].
-// One CTA = one 64-wide slab of the (outer, inner) index space; thread tile 8 rows x 4 columns (G <= 128).
-constexpr int SKI_MT = 64;
+// mode product: tensor viewed as [outer][G][inner] (inner includes the 16 columns): out[o][i][x] = sum_k T[i][k] in[o][k][x],
+// i.e. per 64-wide slab of the flattened (outer, inner) space one [G x G] . [G x 64] product.  Runs on the tensor cores as a
+// 3xTF32 product (T = T_hi + T_lo and B = B_hi + B_lo with round-to-nearest tf32 parts; T_lo B_lo, 2^-22 relative, is dropped):
+// fp32-level accuracy at a small multiple of the tf32 rate, so the pass is bound by streaming the grid block, not by FMAs
+// (the fp32 CUDA-core version of this kernel took 249 us per pass at G = 100, M = 10^6: 13 TFLOP/s).  Warp-level
+// mma.sync.m16n8k8 is the right tool for these skinny products (M = G <= 128 rows, one 64-column slab per CTA step): there is
+// no accumulator reuse across slabs for a tcgen05 / TMEM pipeline to amortise.
+constexpr int SKI_MT = 64;          // slab width (positions)
+constexpr int SKI_BP = SKI_MT + 8;  // pitch of the staged slab: 72 = 8 mod 32 -> conflict-free B fragments
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// shared memory: T [GM][TPITCH] fp32 (rows and columns padded with zeros to GM = 16 ceil(G/16), GK = 8 ceil(G/8); TPITCH = GK + 4
+// = 12 mod 32 for G = 100: conflict-free A fragments; split into hi / lo when a fragment is loaded), the staged slab as
+// B_hi / B_lo [GK][SKI_BP] (split once while staging: seven warps read every value)
 __global__ void __launch_bounds__(256)
 ski_mode_kernel(const float* __restrict__ T, int G, const float* __restrict__ in, float* __restrict__ out, int64_t inner, int64_t total,
                 int64_t nslab) {
   extern __shared__ __align__(16) float smm[];
-  float* Ts = smm;                         // [G][G + 1]
-  float* Bs = smm + (size_t)G * (G + 1);   // [G][64], moved up to the next 16-byte boundary
-  Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Bs) + 15) & ~(uintptr_t)15);
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int e = tid; e < G * G; e += 256) Ts[(e / G) * (G + 1) + (e % G)] = T[e];
+  const int GM = (G + 15) & ~15, GK = (G + 7) & ~7, TP_ = GK + 4;
+  float* Ts = smm;                                                         // [GM][TP_]
+  uint32_t* Bh = reinterpret_cast<uint32_t*>(Ts + (size_t)GM * TP_);        // [GK][SKI_BP]
+  uint32_t* Bl = Bh + (size_t)GK * SKI_BP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < GM; r += 8)
+    for (int c = lane; c < TP_; c += 32) Ts[r * TP_ + c] = (r < G && c < G) ? T[r * G + c] : 0.f;
+  const int gr = lane >> 2, gc = lane & 3;      // fragment coordinates
+  const int nmt = GM / 16, nks = GK / 8;
+  const uint32_t inner32 = (uint32_t)inner, total32 = (uint32_t)total;   // the host checks total < 2^31
+  const int j4 = tid & 15, kst = tid >> 4;       // staging: this thread's float4 column of the slab, first k row
   for (int64_t slab = blockIdx.x; slab < nslab; slab += gridDim.x) {
     // slab -> 64 consecutive positions q = o * inner + x of the flattened (outer, inner) space, q < total = outer * inner
-    const int64_t q0 = slab * SKI_MT;
+    const uint32_t q0 = (uint32_t)slab * SKI_MT;
     __syncthreads();
-    for (int e = tid; e < G * (SKI_MT / 4); e += 256) {
-      const int k = e / (SKI_MT / 4), j4 = e % (SKI_MT / 4);
-      const int64_t q = q0 + j4 * 4;       // inner is a multiple of 16, so 4 consecutive positions share o
-      float4 v = make_float4(0, 0, 0, 0);
-      if (q < total) {
-        const int64_t o = q / inner, x = q % inner;
-        v = *reinterpret_cast<const float4*>(in + (o * G + k) * inner + x);
-      }
-      *reinterpret_cast<float4*>(&Bs[k * SKI_MT + j4 * 4]) = v;
-    }
-    __syncthreads();
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int row0 = ty * 8;
-    for (int k = 0; k < G; ++k) {
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k * SKI_MT + tx * 4]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = (row0 + i < G) ? Ts[(row0 + i) * (G + 1) + k] : 0.f;
-        acc[i][0] = fmaf(a, b.x, acc[i][0]); acc[i][1] = fmaf(a, b.y, acc[i][1]);
-        acc[i][2] = fmaf(a, b.z, acc[i][2]); acc[i][3] = fmaf(a, b.w, acc[i][3]);
+    {
+      // 4 consecutive positions share o (inner is a multiple of 16): one division per thread and slab, then a constant stride per k
+      const uint32_t q = q0 + (uint32_t)j4 * 4;
+      const bool live = q < total32;
+      const uint32_t o = live ? q / inner32 : 0u, x = live ? q - o * inner32 : 0u;
+      const float* src = in + ((size_t)o * G) * inner + x;
+      for (int k = kst; k < GK; k += 16) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (live && k < G) v = *reinterpret_cast<const float4*>(src + (size_t)k * inner);
+        uint4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - __uint_as_float(h.x)); l.y = tf32_rna(v.y - __uint_as_float(h.y));
+        l.z = tf32_rna(v.z - __uint_as_float(h.z)); l.w = tf32_rna(v.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(&Bh[k * SKI_BP + j4 * 4]) = h;
+        *reinterpret_cast<uint4*>(&Bl[k * SKI_BP + j4 * 4]) = l;
       }
     }
-    const int64_t q = q0 + tx * 4;
-    if (q < total) {
-      const int64_t o = q / inner, x = q % inner;
+    __syncthreads();
+    // warp tile: 2 row tiles (32 output rows) x 4 column tiles (32 positions): every B fragment feeds two row tiles, every A
+    // fragment four column tiles (one row tile x 8 column tiles per warp needed 1.5 shared-memory loads per MMA)
+    const int nh = warp & 1;                       // which half of the slab's 64 positions
+    for (int mp = warp >> 1; 2 * mp < nmt; mp += 4) {
+      const bool two = 2 * mp + 1 < nmt;
+      float acc[2][4][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (row0 + i < G)
-          *reinterpret_cast<float4*>(out + (o * G + row0 + i) * inner + x) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[m][nt][j] = 0.f;
+      const float* tp = Ts + (size_t)(mp * 32 + gr) * TP_ + gc;
+      for (int ks = 0; ks < nks; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float* t2 = tp + (size_t)(two ? m : 0) * 16 * TP_;      // a missing second row tile re-reads the first (discarded)
+          const float a[4] = {t2[k0], t2[k0 + 8 * TP_], t2[k0 + 4], t2[k0 + 8 * TP_ + 4]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { ah[m][j] = tf32_rna(a[j]); al[m][j] = tf32_rna(a[j] - __uint_as_float(ah[m][j])); }
+        }
+        const uint32_t* bh = Bh + (size_t)(k0 + gc) * SKI_BP + nh * 32 + gr;
+        const uint32_t* bl = Bl + (size_t)(k0 + gc) * SKI_BP + nh * 32 + gr;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t bh0 = bh[nt * 8], bh1 = bh[nt * 8 + 4 * SKI_BP], bl0 = bl[nt * 8], bl1 = bl[nt * 8 + 4 * SKI_BP];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            mma_tf32_16x8x8(acc[m][nt], al[m], bh0, bh1);   // small terms first
+            mma_tf32_16x8x8(acc[m][nt], ah[m], bl0, bl1);
+            mma_tf32_16x8x8(acc[m][nt], ah[m], bh0, bh1);
+          }
+        }
+      }
+      // C fragment: (row gr, cols 2 gc, 2 gc + 1) and (row gr + 8, same cols) of every 8-column tile
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (m == 1 && !two) break;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t q = q0 + (uint32_t)(nh * 32 + nt * 8 + 2 * gc);
+          if (q < total32) {
+            const uint32_t o = q / inner32, x = q - o * inner32;
+            const int r0 = mp * 32 + m * 16 + gr;
+            float* dst = out + ((size_t)o * G + r0) * inner + x;
+            if (r0 < G) *reinterpret_cast<float2*>(dst) = make_float2(acc[m][nt][0], acc[m][nt][1]);
+            if (r0 + 8 < G) *reinterpret_cast<float2*>(dst + 8 * (size_t)inner) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+          }
+        }
+      }
     }
   }
 }
@@ -383,6 +509,11 @@ __global__ void __launch_bounds__(256) ski_dot_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
 
+static size_t ski_mode_smem(int G) {
+  const size_t GM = (G + 15) & ~15, GK = (G + 7) & ~7;
+  return sizeof(float) * (GM * (GK + 4) + 2 * GK * SKI_BP);
+}
+
 static SkiTiles ski_tiles_of(const gp_ski_state* s, int d) {
   SkiTiles tl;
   tl.ntiles = s->ntiles;
@@ -397,7 +528,9 @@ static int ski_bucket_points(gp_plan* p, const SkiGeom& g) {
   const int d = g.d;
   const int64_t n = p->n1;
   GP_REQUIRE(n < ((int64_t)1 << 31), GP_E_SHAPE, "SKI: n too large");
-  static const int edge_by_d[SKI_MAXD + 1] = {0, 256, 32, 8, 3};   // (E + 3)^d nodes x 64 B <= 85 KB of shared memory
+  // (E + 3)^d nodes x 64 B of shared memory per CTA: 4 / 23 / 22 / 40 KB -> 5 to 8 CTAs per SM hide the dependent
+  // shared-memory read-modify-write chain of the scatter and the per-point loads (E = 8 at d = 3 -- 85 KB, 2 CTAs per SM -- was 3x slower)
+  static const int edge_by_d[SKI_MAXD + 1] = {0, 64, 16, 4, 2};
   int64_t nt = 1;
   for (int i = 0; i < d; ++i) {
     s->tile_edge[i] = edge_by_d[d];
@@ -446,10 +579,10 @@ static int ski_tiled_attrs(gp_plan* p) {
   }
   return GP_OK;
 }
-// CTAs per tile: ~1024 points each on average (no host read-back of the real counts: the split only balances load)
+// CTAs per tile: ~256 points each on average (no host read-back of the real counts: the split only balances load)
 static int ski_tile_parts(const gp_plan* p) {
   const int64_t avg = p->n1 / std::max(1, p->ski->ntiles);
-  return (int)std::min<int64_t>(256, std::max<int64_t>(1, cdiv(avg, 1024)));
+  return (int)std::min<int64_t>(1024, std::max<int64_t>(1, cdiv(avg, 256)));
 }
 // shared memory of one tile's node block
 static size_t ski_tile_smem(const gp_ski_state* s, int d) {
@@ -525,9 +658,9 @@ static int ski_matmul_d(gp_plan* p, const float* V16, int t, float* OUT16) {
   GP_REQUIRE(tsm <= (size_t)SKI_TILE_SMEM, GP_E_SHAPE, "SKI: tile block of %zu bytes does not fit in shared memory", tsm);
   GP_CHECK(ski_tiled_attrs<D>(p));
   const int parts = ski_tile_parts(p);
-  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 4 * (int64_t)p->n_sm);
+  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 16 * (int64_t)p->n_sm);
   GP_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * g.M * TP, st));
-  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, V16, A);
+  ski_scatter_tiled_kernel<D><<<tgrid, SKI_SC_THREADS, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, V16, A);
   size_t toff = 0;
   float* cur = A;
   float* nxt = B;
@@ -536,8 +669,9 @@ static int ski_matmul_d(gp_plan* p, const float* V16, int t, float* OUT16) {
     const int64_t inner = g.stride[i] * TP;                // elements after mode i (incl. the 16 columns)
     const int64_t total = g.M / G * TP;                    // positions of the flattened (outer, inner) space
     const int64_t nslab = cdiv(total, SKI_MT);
-    const size_t sh = sizeof(float) * ((size_t)G * (G + 1) + 4 + (size_t)G * SKI_MT);
-    ski_mode_kernel<<<(unsigned)std::min<int64_t>(nslab, 8 * p->n_sm), 256, sh, st>>>(s->T.as<float>() + toff, G, cur, nxt, inner, total, nslab);
+    const size_t sh = ski_mode_smem(G);
+    GP_REQUIRE(total < ((int64_t)1 << 31), GP_E_SHAPE, "SKI: grid block too large");
+    ski_mode_kernel<<<(unsigned)std::min<int64_t>(nslab, 2 * p->n_sm), 256, sh, st>>>(s->T.as<float>() + toff, G, cur, nxt, inner, total, nslab);
     toff += (size_t)G * G;
     std::swap(cur, nxt);
   }
@@ -567,7 +701,7 @@ static int ski_bilinear_d(gp_plan* p, const float* L16, const float* R16, double
   const size_t tsm = ski_tile_smem(s, D);
   GP_CHECK(ski_tiled_attrs<D>(p));
   const int parts = ski_tile_parts(p);
-  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 4 * (int64_t)p->n_sm);
+  const unsigned tgrid = (unsigned)std::min<int64_t>((int64_t)tl.ntiles * parts, 16 * (int64_t)p->n_sm);
   GP_CHECK(s->gridC.ensure(sizeof(float) * g.M * TP));
   GP_CHECK(s->gridD.ensure(sizeof(float) * g.M * TP));
   GP_CHECK(p->misc.ensure(sizeof(double) * DOT_BLOCKS * (D + 1)));
@@ -576,8 +710,8 @@ static int ski_bilinear_d(gp_plan* p, const float* L16, const float* R16, double
   double* part = p->misc.as<double>();
   GP_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * g.M * TP, st));
   GP_CUDA(cudaMemsetAsync(B, 0, sizeof(float) * g.M * TP, st));
-  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, L16, A);
-  ski_scatter_tiled_kernel<D><<<tgrid, 256, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, R16, B);
+  ski_scatter_tiled_kernel<D><<<tgrid, SKI_SC_THREADS, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, L16, A);
+  ski_scatter_tiled_kernel<D><<<tgrid, SKI_SC_THREADS, tsm, st>>>(s->first_s.as<int>(), s->wts_s.as<float>(), s->perm.as<int>(), s->tile_off.as<int>(), g, tl, parts, R16, B);
   p->launches += 2;
   for (int term = 0; term <= D; ++term) {          // term 0: K_uu ; term 1 + i: derivative factor in dimension i
     size_t toff = 0;
@@ -588,10 +722,11 @@ static int ski_bilinear_d(gp_plan* p, const float* L16, const float* R16, double
       const int64_t inner = g.stride[i] * TP;
       const int64_t tot = g.M / G * TP;
       const int64_t nslab = cdiv(tot, SKI_MT);
-      const size_t sh = sizeof(float) * ((size_t)G * (G + 1) + 4 + (size_t)G * SKI_MT);
+      const size_t sh = ski_mode_smem(G);
       const float* Tm = ((term == 1 + i) ? s->dT.as<float>() : s->T.as<float>()) + toff;
       float* out = bufs[i & 1];
-      ski_mode_kernel<<<(unsigned)std::min<int64_t>(nslab, 8 * p->n_sm), 256, sh, st>>>(Tm, G, cur, out, inner, tot, nslab);
+      GP_REQUIRE(tot < ((int64_t)1 << 31), GP_E_SHAPE, "SKI: grid block too large");
+      ski_mode_kernel<<<(unsigned)std::min<int64_t>(nslab, 2 * p->n_sm), 256, sh, st>>>(Tm, G, cur, out, inner, tot, nslab);
       cur = out;
       toff += (size_t)G * G;
     }
@@ -613,7 +748,7 @@ static int ski_bilinear_d(gp_plan* p, const float* L16, const float* R16, double
 int ski_bilinear(gp_plan* p, const float* L16, const float* R16, double* total) {
   static bool attr_done[64] = {};
   if (!attr_done[p->device & 63]) {
-    GP_CUDA(cudaFuncSetAttribute(ski_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    GP_CUDA(cudaFuncSetAttribute(ski_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_done[p->device & 63] = true;
   }
   switch (p->d) {
@@ -631,7 +766,7 @@ int ski_kmv_partials(gp_plan* p, const float* V16, const int* done_flag) {
   (void)done_flag;   // the products of a finished mBCG are cheap no-ops for the dense kernels; here they simply run
   static bool attr_done[64] = {};
   if (!attr_done[p->device & 63]) {
-    GP_CUDA(cudaFuncSetAttribute(ski_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    GP_CUDA(cudaFuncSetAttribute(ski_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_done[p->device & 63] = true;
   }
   switch (p->d) {

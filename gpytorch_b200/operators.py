@@ -433,7 +433,72 @@ class SKIKernelLinearOperator(KernelLinearOperator):
         raise NotImplementedError("diagonal of the SKI operator")
 
     def __getitem__(self, index):
-        raise NotImplementedError("slicing the SKI operator")
+        """Rows / columns of the interpolated operator: K[r, c] = W[r] K_uu W[c]^T (the reference slices the interpolation
+        indices / values of InterpolatedLinearOperator).  Used by the prediction strategy on the joint train + test operator."""
+        if not isinstance(index, tuple):
+            index = (index, slice(None))
+        ri, ci = index
+        n = self.x1.size(0)
+        ar = torch.arange(n, device=self.device)
+        rows = ar[ri].reshape(-1)
+        cols = ar[ci].reshape(-1)
+        sub = _SKISliceOperator(self, rows, cols)
+        return sub.to_dense()[0] if isinstance(ri, int) else sub
+
+
+class _SKISliceOperator:
+    """K_ski[rows, cols] of a square SKI operator, never materialised: a product zero-pads the right-hand side to the full point
+    set, runs the parent's scatter / mode products / gather, and keeps the requested rows (evaluation mode: no autograd)."""
+
+    def __init__(self, parent, rows, cols):
+        self.parent, self.rows, self.cols = parent, rows, cols
+
+    @property
+    def shape(self):
+        return torch.Size([self.rows.numel(), self.cols.numel()])
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    @property
+    def device(self):
+        return self.parent.device
+
+    @property
+    def dtype(self):
+        return self.parent.dtype
+
+    def evaluate_kernel(self):
+        return self
+
+    def _transpose_nonbatch(self):
+        return _SKISliceOperator(self.parent, self.cols, self.rows)      # the parent is symmetric
+
+    t = _transpose_nonbatch
+
+    def transpose(self, dim1, dim2):
+        return self if dim1 % 2 == dim2 % 2 else self._transpose_nonbatch()
+
+    def matmul(self, rhs):
+        vec = rhs.dim() == 1
+        r2 = (rhs.unsqueeze(-1) if vec else rhs).detach().float()
+        if r2.size(0) != self.cols.numel():
+            raise RuntimeError(f"LinearOperator (size={tuple(self.shape)}) cannot be multiplied with right-hand-side Tensor "
+                               f"(size={tuple(rhs.shape)})")
+        plan = self.parent.plan(getattr(self.parent, "_last_noise", 0.0))
+        outs = []
+        for c0 in range(0, r2.size(1), 16):
+            full = torch.zeros(self.parent.x1.size(0), min(16, r2.size(1) - c0), device=self.device)
+            full[self.cols] = r2[:, c0:c0 + 16]
+            outs.append(plan.kmv(full)[self.rows])
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
+        return out.squeeze(-1) if vec else out
+
+    __matmul__ = matmul
+    _matmul = matmul
+
+    def to_dense(self):
+        return self.matmul(torch.eye(self.cols.numel(), device=self.device))
 
 
 class _KernelMatmul(torch.autograd.Function):

@@ -187,3 +187,42 @@ def test_ski_training_step_through_the_api(cuda_dev):
     assert raw_grad(k.base_kernel.base_kernel.raw_lengthscale) == pytest.approx(ls.grad.item(), rel=0.2, abs=3e-3)
     assert raw_grad(k.raw_outputscale) == pytest.approx(osc.grad.item(), rel=0.2, abs=3e-3)
     assert raw_grad(lik.raw_noise) == pytest.approx(nz.grad.item(), rel=0.2, abs=3e-3)
+
+
+def test_ski_prediction_through_the_api(cuda_dev):
+    """Posterior mean / covariance of a KISS-GP model: the joint train + test operator is sliced (W[r] K_uu W[c]^T) -- against the dense
+    posterior built from the oracle's interpolated covariance of the joint point set."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+
+    n, m, d, sizes, ls0, os0, nz0 = 1500, 30, 2, [24, 24], 0.3, 1.1, 0.2
+    x, y = om.synthetic_problem(n, d, 8, torch.float32)
+    xt = torch.rand(m, d, generator=torch.Generator().manual_seed(2))
+    axes, lo, step = _grid(sizes, [(0.0, 1.0)] * d)
+    lik = gp.likelihoods.GaussianLikelihood().to(cuda_dev)
+    lik.noise = nz0
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(x.to(cuda_dev), y.to(cuda_dev), lik)
+            self.mean_module = gp.means.ZeroMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.GridInterpolationKernel(gp.kernels.RBFKernel(), grid_size=24, num_dims=2,
+                                                                                       grid_bounds=[(0.0, 1.0)] * 2))
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.base_kernel.lengthscale = ls0
+    model.covar_module.outputscale = os0
+    model.eval(); lik.eval()
+    with torch.no_grad(), settings.eval_cg_tolerance(1e-5):
+        pred = model(xt.to(cuda_dev))
+    xj = torch.cat([x, xt]).double()
+    Kj = ski.ski_matmul("rbf", xj, [a.double() for a in axes], ls0, os0, torch.eye(n + m, dtype=torch.float64))
+    Kj = 0.5 * (Kj + Kj.t())
+    Lc = torch.linalg.cholesky(Kj[:n, :n] + nz0 * torch.eye(n, dtype=torch.float64))
+    mean_ref = Kj[n:, :n] @ torch.cholesky_solve(y.double().unsqueeze(-1), Lc).squeeze(-1)
+    cov_ref = Kj[n:, n:] - Kj[n:, :n] @ torch.cholesky_solve(Kj[:n, n:], Lc)
+    assert rel(pred.mean, mean_ref) < 2e-3
+    assert rel(pred.covariance_matrix, cov_ref) < 2e-2
