@@ -4,28 +4,31 @@
 // functions/rbf_covariance.py:14-19), the Matern poly*exp passes (functions/matern_covariance.py:21-47) and the dense
 // K @ V inside linear_cg (lazy/lazy_evaluated_kernel_tensor.py:245-276).  K never exists in HBM.
 //
-// What changed against kmv_tc.cu (round 1, "v16": 0.92 ms at C2, profiles/NOTES_r01.md) and why:
-//  * One CTA per SM owns a 256-row block: epilogue warpgroup w (4 warps) owns the 128-row half w, both halves share ONE
-//    B / V stream, so the L2 -> SMEM traffic per K tile halves (v16 streamed ~3 GB per launch).
-//  * Each warpgroup ALTERNATES between two private TMEM slots (tile u in slot u & 1).  In v16 a warpgroup was bound to one
-//    slot and waited ~1500 cycles per tile for  p_full -> GEMM2 -> GEMM1 -> s_full ; now GEMM2(u-1) + GEMM1(u+1) of the other
-//    slot run underneath the epilogue of tile u, and the epilogue is software-pipelined ACROSS tiles (the S loads and the
-//    first MUFU group of tile u+1 are issued inside the last steps of tile u), so the MUFU stream never drains.
+// What changed against kmv_tc.cu (round 1, "v16": 0.92 ms at C2, profiles/NOTES_r01.md) and why (profiles/NOTES_r02.md):
+//  * One CTA per SM owns a 256-row block: epilogue warpgroup w owns the 128-row half w, both halves share ONE B / V stream, so the
+//    L2 -> SMEM traffic per K tile halves (v16 streamed ~3 GB per launch).
+//  * Each row half ALTERNATES between two private TMEM slots (tile u in slot u & 1) and has its OWN issuer warp: GEMM2(u-1) +
+//    GEMM1(u+1) of the other slot run underneath the epilogue of tile u.  The ~1000 cycles per tile that v16 lost were the single
+//    issuer warp's scalar instruction stream, not the tensor pipe: running descriptors, a looped GEMM1, polling waits and the
+//    issuers as the oldest warps of their sub-partitions brought the turn-around down to the epilogue time of a tile.
+//  * No software pipelining across tiles in the epilogue: S(u+1) is requested only after P(u) is released (prefetching it
+//    lengthens the release -> s_full turn-around it competes with; measured).
 //  * GEMM1 takes its A operand from TMEM (TS mode): the 128 x KP tile of a row half is constant for the whole CTA, SS mode
 //    re-read it from shared memory for every tile (48 cycles per MMA, smem-bandwidth bound; TS: 32).  KP <= 48 only; wider
 //    feature vectors (KP <= 64) keep A in shared memory.
-//  * A quarter (RBF) of the ex2 evaluations run as a degree-5 polynomial on the FMA pipe (Cody-Waite split with the
-//    magic-number rounding trick, packed f32x2 arithmetic), the rest on the MUFU: the kernel is transcendental-bound and the
-//    FMA pipe was 11 % busy.  Max relative error of the polynomial 1.8e-7 (MUFU.EX2: ~1.7e-7).
-//  * O is a single 16-column accumulator per warpgroup (V_hi and V_lo products accumulate into the same columns), folded
-//    into fp32 registers once per tile inside the last step of the NEXT tile (its GEMM2 completed a tile-time earlier).
+//  * 0, 2 or 4 of every 8 ex2 evaluations (template NPOLY) can run as a degree-5 polynomial on the FMA pipe (Cody-Waite split
+//    with the magic-number rounding trick, packed f32x2 arithmetic; max relative error 1.8e-7, MUFU.EX2: ~1.7e-7): default 2 for
+//    Matern (sqrt + ex2 per entry), 0 for RBF (not MUFU-bound any more: the extra issue slots cost more than they save).
+//  * O is a single 16-column accumulator per row half (V_hi and V_lo products accumulate into the same columns), folded into
+//    fp32 registers once per tile, late in the NEXT tile, after waiting for o_full of the tile it belongs to.
 //
 // TMEM columns (512, one CTA per SM):
 //   slot (w, b) at (2w + b) * 96: S / P_hi [0,64) + P_lo (bf16 pairs) [64,96)        -> [0, 384)
 //   O(w) at 384 + 16 w                                                               -> [384, 416)
 //   A(w) at 416 + 48 w  (TS mode, KP <= 48)                                          -> [416, 512)
-// Warp roles: 0-3 epilogue warpgroup 0, 4-7 epilogue warpgroup 1, 8 TMA producer, 9 / 10 MMA issuers of warpgroup 0 / 1
-// (warp 9 also allocates TMEM).
+// Warp roles (640 threads): 0 / 1 MMA issuers of row half 0 / 1 (warp 0 also allocates TMEM), 2 TMA producer, 3 trace observer
+// (trace builds only), 4-19 epilogue: (warp - 4) >> 3 = row half, ((warp - 4) >> 2) & 1 = column half of the 64-column tile,
+// warp & 3 = TMEM lane quadrant.
 #include "gp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -256,7 +259,7 @@ kmv_tc2_kernel(const float* __restrict__ XA, const float* __restrict__ XB, const
       }
     }
   } else if (warp < 2) {
-    // ===================== MMA issuers: warp 9 serves warpgroup 0, warp 10 warpgroup 1 ==========
+    // ===================== MMA issuers: warp 0 serves row half 0, warp 1 row half 1 ==========
     // Program order per issuer:  G1(w,0) G1(w,1) ; for u: wait P(w,u) -> GEMM2(w,u) -> GEMM1(w,u+2).
     // One thread issues everything of a warpgroup, so the tensor pipe orders GEMM2(w,u) (reads P in slot u&1) before
     // GEMM1(w,u+2) (overwrites it), and GEMM2(w,u) (overwrites O(w)) comes after the epilogue's arrive on p_full(w,u), which

@@ -304,3 +304,25 @@ def test_additive_kernel_protocol_without_compute():
         a + a[:10]
     with pytest.raises(RuntimeError, match="must be kernels"):
         gp.kernels.AdditiveKernel(gp.kernels.RBFKernel(), 3.0)
+
+
+def test_ski_operator_slicing_protocol_without_compute():
+    """Rows / columns of the interpolated operator stay lazy (prediction slices the joint train + test operator):
+    shapes, transposes and the size check need no device work; products need the CUDA engine."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200.operators import SKIKernelLinearOperator
+
+    x = torch.rand(50, 2)
+    k = gp.kernels.ScaleKernel(gp.kernels.GridInterpolationKernel(gp.kernels.RBFKernel(), grid_size=12, num_dims=2, grid_bounds=[(0.0, 1.0)] * 2))
+    op = k(x)
+    assert isinstance(op, SKIKernelLinearOperator) and op.shape == torch.Size([50, 50])
+    ks = op[40:, :40]
+    assert ks.shape == torch.Size([10, 40]) and ks.t().shape == torch.Size([40, 10]) and ks.transpose(-1, -2).shape == torch.Size([40, 10])
+    assert ks.transpose(-1, -1) is ks and ks.evaluate_kernel() is ks and ks.device == x.device
+    assert op[torch.tensor([1, 3, 5]), :].shape == torch.Size([3, 50])
+    with pytest.raises(RuntimeError, match="cannot be multiplied"):
+        ks.matmul(torch.rand(7, 2))
+    with pytest.raises(RuntimeError):          # the product itself: CUDA only
+        ks.matmul(torch.rand(40, 2))
+    with pytest.raises(NotImplementedError):
+        op + op                                  # interpolated operators are not summed on the accelerated path
