@@ -683,6 +683,8 @@ class AddedDiagLinearOperator:
     def _probes(self, lt, tp):
         n = self.shape[0]
         seed = settings.probe_seed.value()
+        if seed is None and settings.deterministic_probes.on():
+            seed = settings.deterministic_probes.seed       # one set of base samples for every estimate while the flag is on
         gen = None
         if seed is not None:
             gen = torch.Generator(device=self.device).manual_seed(int(seed))
@@ -719,8 +721,12 @@ class AddedDiagLinearOperator:
 
     def root_inv_decomposition(self, initial_vectors=None):
         """Lanczos root of K_hat^{-1}: R with R R^T ~= K_hat^{-1} (exact_prediction_strategies.py:268-272)."""
-        p = self._plan()
         n = self.shape[0]
+        if settings.fast_computations.covar_root_decomposition.off():
+            # exact root through the dense Cholesky factor: K_hat = L L^T  =>  K_hat^{-1} = L^{-T} L^{-1}
+            chol = self._dense_cholesky()
+            return torch.linalg.solve_triangular(chol.transpose(-1, -2), torch.eye(n, device=self.device, dtype=chol.dtype), upper=True)
+        p = self._plan()
         init = initial_vectors if initial_vectors is not None else torch.randn(n, device=self.device)
         if init.dim() == 2:
             init = init[:, 0]
@@ -853,16 +859,30 @@ def _run_cg(op: AddedDiagLinearOperator, rhs, n_tridiag, w):
     """linear_cg over <= 16 columns per call."""
     p = op._plan()
     outs, tmat, iters = [], None, 0
+    max_iter = settings.max_cg_iterations.value()
+    if settings.terminate_cg_by_size.on():
+        max_iter = min(max_iter, op.shape[0])
     for c0 in range(0, rhs.size(1), 16):
         blk = rhs[:, c0 : c0 + 16].contiguous()
         nt = n_tridiag if c0 == 0 else 0
-        s, tm, info = p.mbcg(blk, nt, _cg_tolerance(), settings.max_cg_iterations.value(),
+        s, tm, info = p.mbcg(blk, nt, _cg_tolerance(), max_iter,
                              settings.max_lanczos_quadrature_iterations.value(), w)
         outs.append(s)
         iters = max(iters, info.iters)
         if nt:
             tmat = tm
+    if settings.verbose_linalg.on():
+        settings.verbose_linalg.logger.debug(
+            f"Running CG on a {tuple(rhs.shape)} RHS for {iters} iterations (tol={_cg_tolerance()}). Output: {tuple(rhs.shape)}.")
     return (outs[0] if len(outs) == 1 else torch.cat(outs, -1)), tmat, iters
+
+
+def _dense_branch(n: int, fast_flag) -> bool:
+    """The reference's Cholesky branch: small systems (max_cholesky_size) or the Krylov path switched off (fast_computations)."""
+    dense = n <= settings.max_cholesky_size.value() or fast_flag.off()
+    if dense and settings.verbose_linalg.on():
+        settings.verbose_linalg.logger.debug(f"Running Cholesky on a matrix of size {(n, n)}.")
+    return dense
 
 
 class _Solve(torch.autograd.Function):
@@ -871,7 +891,8 @@ class _Solve(torch.autograd.Function):
         vec = rhs.dim() == 1
         r2 = (rhs.unsqueeze(-1) if vec else rhs).detach().float().contiguous()
         n = op.shape[0]
-        if n <= settings.max_cholesky_size.value():
+        ctx.dense = _dense_branch(n, settings.fast_computations.solves)
+        if ctx.dense:
             chol = op._dense_cholesky()
             sol = torch.cholesky_solve(r2, chol)
         else:
@@ -886,8 +907,7 @@ class _Solve(torch.autograd.Function):
         op = ctx.op
         (sol,) = ctx.saved_tensors
         g = (grad_out.unsqueeze(-1) if ctx.vec else grad_out).contiguous()
-        n = op.shape[0]
-        if n <= settings.max_cholesky_size.value():
+        if ctx.dense:
             gsol = torch.cholesky_solve(g, op._dense_cholesky())
         else:
             w, _, _ = op._preconditioner()
@@ -914,7 +934,7 @@ class _InvQuadLogdet(torch.autograd.Function):
         ctx.op, ctx.want_logdet, ctx.has_rhs = op, want_logdet, rhs is not None
         nr = 0 if rhs is None else rhs.size(1)
         r = None if rhs is None else rhs.detach().float().contiguous()
-        if n <= settings.max_cholesky_size.value():  # the reference's dense branch (not the accelerated path)
+        if _dense_branch(n, settings.fast_computations.log_prob):  # the reference's dense branch (not the accelerated path)
             chol = op._dense_cholesky()
             sol = torch.cholesky_solve(r, chol) if r is not None else None
             iq = (sol * r).sum(-2) if r is not None else torch.zeros(0, device=dev)

@@ -411,3 +411,54 @@ def test_c4_batched_exact_gp_through_api(cuda_dev):
     gl = model.covar_module.base_kernel.raw_lengthscale.grad
     assert gl is not None and tuple(gl.shape) == (B, 1, 1) and torch.isfinite(gl).all() and (gl != 0).all()
     assert lik.noise_covar.raw_noise.grad is not None and torch.isfinite(lik.noise_covar.raw_noise.grad).all()
+
+
+def test_solver_path_knobs_fast_computations_deterministic_probes_terminate_by_size(cuda_dev):
+    """settings.fast_computations(log_prob=False, solves=False) forces the dense Cholesky branch above max_cholesky_size (MLL then
+    equals the dense value); deterministic_probes re-uses one set of probes (bit-identical stochastic estimates); terminate_cg_by_size
+    caps the iterations at n."""
+    import gpytorch_b200 as gp
+    from gpytorch_b200 import settings
+    from gpytorch_b200.operators import ConstantDiagLinearOperator, KernelLinearOperator
+
+    n, d = 1500, 3
+    x, y = om.synthetic_problem(n, d, 3, torch.float32)
+    xd, yd = x.to(cuda_dev), y.to(cuda_dev)
+    lik = gp.likelihoods.GaussianLikelihood().to(cuda_dev)
+    lik.noise = 0.15
+
+    class M(gp.models.ExactGP):
+        def __init__(self):
+            super().__init__(xd, yd, lik)
+            self.mean_module = gp.means.ZeroMean()
+            self.covar_module = gp.kernels.ScaleKernel(gp.kernels.RBFKernel())
+
+        def forward(self, xx):
+            return gp.distributions.MultivariateNormal(self.mean_module(xx), self.covar_module(xx))
+
+    model = M().to(cuda_dev)
+    model.covar_module.base_kernel.lengthscale = 0.6
+    model.covar_module.outputscale = 1.2
+    mll = gp.mlls.ExactMarginalLogLikelihood(lik, model)
+    model.train(); lik.train()
+    dense = om.mll_cholesky("rbf", x.double(), y.double(), 0.0, 0.6, 1.2, 0.15).mll
+    with torch.no_grad(), settings.fast_computations(log_prob=False, solves=False):
+        exact = mll(model(xd), yd).item()
+    assert exact == pytest.approx(dense, rel=2e-4, abs=2e-5)
+    with torch.no_grad(), settings.deterministic_probes(True):
+        a = mll(model(xd), yd).item()
+        b = mll(model(xd), yd).item()
+    assert a == b and abs(a - dense) < 0.03          # 10 Rademacher probes, no preconditioner at n = 1500: stochastic log-det
+    with torch.no_grad():
+        c = mll(model(xd), yd).item()
+        e = mll(model(xd), yd).item()
+    assert c != e                                   # fresh probes every evaluation without the flag
+    # terminate_cg_by_size: an unreachable tolerance stops at n iterations instead of max_cg_iterations
+    m = 200
+    op = KernelLinearOperator(xd[:m].contiguous(), None, "rbf", torch.tensor(0.6, device=cuda_dev), torch.tensor(1.2, device=cuda_dev))
+    khat = op + ConstantDiagLinearOperator(torch.tensor(1e-3, device=cuda_dev), m)
+    with torch.no_grad(), warnings.catch_warnings(), settings.max_cholesky_size(0), settings.cg_tolerance(1e-12), \
+            settings.max_preconditioner_size(0), settings.terminate_cg_by_size(True):
+        warnings.simplefilter("ignore")
+        khat.inv_quad_logdet(yd[:m].unsqueeze(-1), logdet=True)
+    assert khat.last_cg_iters <= m

@@ -39,6 +39,34 @@ def test_settings_context_managers_nest_and_restore():
     assert settings.skip_logdet_forward.off()
 
 
+def test_settings_remaining_reference_knobs():
+    """The knobs the reference re-exports from linear_operator beyond the solver sizes (gpytorch/settings.py:6-31)."""
+    assert settings.terminate_cg_by_size.off() and settings.verbose_linalg.off() and settings.deterministic_probes.off()
+    assert settings.tridiagonal_jitter.value() == 1e-6
+    fc = settings.fast_computations
+    assert fc.covar_root_decomposition.on() and fc.log_prob.on() and fc.solves.on()
+    with fc(log_prob=False):
+        assert fc.log_prob.off() and fc.solves.on() and fc.covar_root_decomposition.on()
+        with fc(solves=False, log_prob=True):
+            assert fc.log_prob.on() and fc.solves.off()
+        assert fc.log_prob.off() and fc.solves.on()
+    assert fc.log_prob.on()
+    with settings.deterministic_probes(True):
+        seed = settings.deterministic_probes.seed
+        assert settings.deterministic_probes.on() and isinstance(seed, int)
+        with settings.deterministic_probes(True):
+            assert settings.deterministic_probes.seed == seed          # one set of probes for the whole region
+    assert settings.deterministic_probes.off() and settings.deterministic_probes.seed is None
+    # hand-over to worker threads: the captured overrides win inside restore(), the thread's own state comes back afterwards
+    with settings.cg_tolerance(0.25), settings.fast_pred_var(True):
+        snap = settings.snapshot()
+    assert settings.cg_tolerance.value() == 1.0 and settings.fast_pred_var.off()
+    with settings.restore(snap):
+        assert settings.cg_tolerance.value() == 0.25 and settings.fast_pred_var.on()
+    assert settings.cg_tolerance.value() == 1.0 and settings.fast_pred_var.off()
+    assert settings.verbose_linalg.logger.name == "LinAlg (Verbose)"
+
+
 def test_constraints_roundtrip():
     v = torch.tensor([0.3, 1.0, 7.5])
     assert torch.allclose(Positive().transform(Positive().inverse_transform(v)), v, atol=1e-6)
