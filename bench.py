@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -453,8 +452,6 @@ def run_c4(args, w):
     torch.cuda.synchronize(dev)
     ms_step = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
-    # serial reference: the same B problems one after the other on one stream (what round 1 did)
-    from gpytorch_b200.operators import BatchLinearOperator
     line = {
         "metric": METRIC, "value": B * 1e3 / ms_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -3,7 +3,6 @@ import math
 
 import torch
 
-from . import settings
 
 
 class MultivariateNormal:

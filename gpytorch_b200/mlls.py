@@ -1,6 +1,4 @@
 """ExactMarginalLogLikelihood (gpytorch/mlls/exact_marginal_log_likelihood.py:54-89)."""
-import torch
-
 from .distributions import MultivariateNormal
 from .likelihoods import _GaussianLikelihoodBase
 from .module import Module

@@ -14,13 +14,9 @@ All arithmetic runs in libgpbbmm (CUDA); torch supplies memory, streams and the 
 """
 from __future__ import annotations
 
-import math
-import warnings
-
 import torch
 
 from . import settings
-from ._lib import NumericalWarning
 from .engine import Plan
 
 
