@@ -94,3 +94,45 @@ def test_ski_approximates_the_exact_kernel():
     exact = ok.kernel_matrix("rbf", x, x, 0.3, 1.0, True) @ v
     approx = ski.ski_matmul("rbf", x, grid, 0.3, 1.0, v)
     assert ((approx - exact).norm() / exact.norm()).item() < 2e-3
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_ski_hyperparameter_gradients_autograd_vs_finite_differences(kind):
+    """The GPU parity test of gp_bilinear_grad on the SKI backend (tests/test_gpu_ski.py) takes its reference from autograd through
+    ski_matmul; pin that reference itself: central finite differences of sum(L * (K_ski R)) in the lengthscale and the outputscale."""
+    g = torch.Generator().manual_seed(3)
+    n, d, sizes = 300, 2, [14, 11]
+    x = torch.rand(n, d, generator=g, dtype=torch.float64)
+    axes = ski.create_grid(sizes, [(0.0, 1.0)] * d, dtype=torch.float64)
+    left = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    right = torch.randn(n, 3, generator=g, dtype=torch.float64)
+
+    def f(ls, osc):
+        return (left * ski.ski_matmul(kind, x, axes, ls, osc, right)).sum()
+
+    ls = torch.tensor([0.4], dtype=torch.float64, requires_grad=True)
+    osc = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+    f(ls, osc).backward()
+    h = 1e-6
+    fd_ls = (f(torch.tensor([0.4 + h], dtype=torch.float64), 1.3) - f(torch.tensor([0.4 - h], dtype=torch.float64), 1.3)) / (2 * h)
+    fd_os = (f(torch.tensor([0.4], dtype=torch.float64), 1.3 + h) - f(torch.tensor([0.4], dtype=torch.float64), 1.3 - h)) / (2 * h)
+    assert ls.grad.item() == pytest.approx(fd_ls.item(), rel=1e-6)
+    assert osc.grad.item() == pytest.approx(fd_os.item(), rel=1e-7)
+
+
+def test_additive_kernel_oracle_mll_matches_dense_cholesky():
+    """Reference for tests/test_gpu_sum.py: the oracle's mBCG evaluation on the dense sum K_1 + K_2 (what AdditiveKernel builds,
+    kernels/kernel.py:612-621) agrees with dense Cholesky; the preconditioner's pivoted Cholesky runs on rows of the sum."""
+    from oracle import mll as om
+
+    n = 600
+    x, y = om.synthetic_problem(n, 4, 1, torch.float64)
+    K = ok.kernel_matrix("rbf", x[:, :2], x[:, :2], 0.5, 0.9, True) + ok.kernel_matrix("matern52", x, x, 1.3, 0.6, True)
+    pn = tuple(a.double() for a in om.make_probe_noise(n, 20, 10, 2))
+    res = om.mll_bbmm("rbf", x, y, 0.0, 1.0, 1.5, 0.2, pn, precond_size=20, min_precond_size=100, tolerance=1e-6, K=K)
+    Lc = torch.linalg.cholesky(K + 0.2 * torch.eye(n, dtype=torch.float64))
+    iq = (y @ torch.cholesky_solve(y.unsqueeze(-1), Lc)).item()
+    ld = 2 * Lc.diagonal().log().sum().item()
+    assert res.inv_quad == pytest.approx(iq, rel=1e-5)
+    assert res.logdet == pytest.approx(ld, rel=0.1)            # 10 probes: stochastic
+    assert res.precond is not None and res.precond.L.shape == (n, 20)
