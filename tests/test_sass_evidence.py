@@ -51,3 +51,28 @@ def test_fused_kernel_and_ski_kernels_have_the_expected_instructions(sass):
         body = _function_bodies(sass, k)
         assert body and "ATOMS.CAST" not in body, f"{k}: fp32 shared-memory atomics are a compare-and-swap loop on sm_100"
     assert "REDG.E.ADD.F32x4" in _function_bodies(sass, "ski_scatter_tiled_kernel")
+
+
+def test_hot_kernels_fit_their_register_budget_without_spills():
+    """Resource usage of the hot kernels: the fused K.V kernel runs 640 threads per CTA (<= 102 registers per thread) and must not
+    spill; the SKI scatter / mode kernels likewise (a local-memory array in the first tiled scatter cost 2.9 GB of L2 traffic)."""
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool) or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or libgpbbmm.so not available")
+    r = subprocess.run([tool, "--dump-resource-usage", LIB], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0
+    lines = r.stdout.splitlines()
+    seen = {"kmv_tc2_kernel": 0, "ski_scatter_tiled_kernelILi3": 0, "ski_mode_kernel": 0, "cg_finishv_wtv_kernel": 0, "cg_update_precond_kernel": 0}
+    for i, line in enumerate(lines):
+        if "Function" not in line:
+            continue
+        for key in seen:
+            if key in line:
+                usage = lines[i + 1]
+                reg = int(re.search(r"REG:(\d+)", usage).group(1))
+                stack = int(re.search(r"STACK:(\d+)", usage).group(1))
+                assert stack == 0, f"{line.strip()}: {stack} bytes of local memory"
+                if key == "kmv_tc2_kernel":
+                    assert reg <= 102, f"{line.strip()}: {reg} registers x 640 threads do not fit one SM"
+                seen[key] += 1
+    assert all(v > 0 for v in seen.values()), seen
